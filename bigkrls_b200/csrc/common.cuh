@@ -1,0 +1,205 @@
+// Shared internals of libbigkrls_b200: context, error plumbing, device buffers, small
+// device helpers (cp.async, DMMA m8n8k4, grid barrier).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include "../../include/bigkrls_b200.h"
+
+namespace bk {
+
+void set_error(const char* fmt, ...);
+
+#define BK_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      bk::set_error("%s:%d CUDA error %s (%s)", __FILE__, __LINE__, cudaGetErrorName(e__), \
+                    cudaGetErrorString(e__));                                           \
+      return BK_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define BK_TRY(call)                 \
+  do {                               \
+    int s__ = (call);                \
+    if (s__ != BK_OK) return s__;    \
+  } while (0)
+
+#define BK_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      bk::set_error(__VA_ARGS__);    \
+      return BK_ERR_ARG;             \
+    }                                \
+  } while (0)
+
+// RAII device buffer (doubles unless stated).  Allocation failures surface as BK_ERR_CUDA.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return BK_ERR_CUDA;
+    }
+    n = count;
+    return BK_OK;
+  }
+  // grow-only
+  int ensure(size_t count) {
+    if (count <= n && p) return BK_OK;
+    return alloc(count);
+  }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s = nullptr;
+  int init(cudaStream_t st) {
+    s = st;
+    BK_CUDA(cudaEventCreate(&a));
+    BK_CUDA(cudaEventCreate(&b));
+    return BK_OK;
+  }
+  ~Timer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, s); }
+  // returns seconds; synchronises the stream
+  double stop() {
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return (double)ms * 1e-3;
+  }
+};
+
+}  // namespace bk
+
+struct bk_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  bk::DevBuf<double> gemm_ws;          // split-K partials
+  bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
+  bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
+  uint64_t n_launches = 0;             // kernels launched through this context (bench "gpu_launches")
+};
+
+namespace bk {
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// 8-byte async global->shared copy; src_bytes in {0, 8}: 0 zero-fills.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem),
+               "r"(src_bytes));
+}
+// 16-byte async copy; src_bytes in {0, 8, 16}; remaining bytes are zero-filled.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem),
+               "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds
+//   A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4) + {0,1}].   SASS: DMMA.8x8x4
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum; `red` must hold >= 32 doubles of shared memory.  All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier for persistent kernels launched with cudaLaunchCooperativeKernel (all
+// CTAs co-resident).  `counter` is monotonically increasing and must be 0 at kernel start;
+// `epoch` is a per-thread register counting barriers passed so far.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  epoch += 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+#endif  // __CUDACC__
+
+// launch-count bookkeeping
+#define BK_LAUNCHED(ctx) ((ctx)->n_launches++)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace bk

@@ -1,0 +1,351 @@
+// FP64 GEMM for sm_100a on the DMMA (mma.sync m8n8k4 f64) tensor path.
+//
+// C (m x n, col-major) = alpha * op(A) * op(B) + beta * C
+//
+// This is the workhorse behind every dense contraction on the hot path: vcov = M Q'
+// (reference src/crossprod.cpp:53), the tall-skinny K-pass K [1 c X X.c] (replaces the
+// N x N temporaries of src/bigderiv_v3.cpp:90-106), Q'y / Q'R, the rank-2b trailing update
+// and the block-reflector back-transform of the eigensolver, and the divide-and-conquer
+// merge GEMMs (replacing LAPACK dsyevd behind src/eigen.cpp:24).
+//
+// Design: CTA tile BM x BN x 16, 3-stage cp.async pipeline into padded shared memory
+// (row strides = 4 mod 16 doubles so that the 8-byte fragment loads of a half-warp hit 16
+// distinct bank pairs), 8 warps, each warp holds (BM/WM) x (BN/WN) accumulators in
+// registers as 8x8 DMMA tiles.  FP64 has no tcgen05 kind, so TMEM/UMMA do not apply; TMA is
+// not used because operands are arbitrary sub-matrix views (odd offsets / leading
+// dimensions break the 16-byte global alignment TMA needs) - cp.async handles both the
+// 16-byte fast path and the 8-byte general path.
+//
+// Variants: transposed operands, batched (array of problem descriptors, blockIdx.z),
+// lower-triangle-only tile skipping (SYRK/SYR2K-like updates), deterministic split-K for
+// short-and-wide reductions (partials to a workspace, fixed-order reduce).
+#include "common.cuh"
+#include "dgemm.cuh"
+
+namespace bk {
+
+static constexpr int BK = 16;
+static constexpr int STAGES = 3;
+static constexpr int KPAD = BK + 4;  // K-major row stride (doubles), 20 = 4 mod 16
+
+template <int BMN>
+struct TileSize {
+  static constexpr int mn_major = BK * (BMN + 4);  // [k][mn], stride BMN+4
+  static constexpr int k_major = BMN * KPAD;       // [mn][k], stride 20
+  static constexpr int max = (mn_major > k_major) ? mn_major : k_major;
+};
+
+// ---- global -> shared tile loaders ---------------------------------------------------------
+// MN-major: logical element (mn, kk) lives at src[(mn0+mn) + (k0+kk)*ld] -> dst[kk*(BMN+4)+mn]
+template <int BMN, int NT, bool VEC>
+__device__ __forceinline__ void load_mn_major(double* dst, const double* __restrict__ src,
+                                              long long ld, int mn0, int k0, int mn_max,
+                                              int k_max) {
+  constexpr int S = BMN + 4;
+  if (VEC) {
+    constexpr int PAIRS = BMN / 2;
+#pragma unroll
+    for (int idx = threadIdx.x; idx < PAIRS * BK; idx += NT) {
+      const int mn = (idx % PAIRS) * 2, kk = idx / PAIRS;
+      const int gm = mn0 + mn, gk = k0 + kk;
+      int valid = (gk < k_max) ? max(0, min(2, mn_max - gm)) : 0;
+      const double* g = valid ? (src + gm + (long long)gk * ld) : src;
+      cp_async16(dst + kk * S + mn, g, valid * 8);
+    }
+  } else {
+#pragma unroll
+    for (int idx = threadIdx.x; idx < BMN * BK; idx += NT) {
+      const int mn = idx % BMN, kk = idx / BMN;
+      const int gm = mn0 + mn, gk = k0 + kk;
+      const bool valid = (gk < k_max) && (gm < mn_max);
+      const double* g = valid ? (src + gm + (long long)gk * ld) : src;
+      cp_async8(dst + kk * S + mn, g, valid ? 8 : 0);
+    }
+  }
+}
+// K-major: logical element (mn, kk) lives at src[(k0+kk) + (mn0+mn)*ld] -> dst[mn*20 + kk]
+template <int BMN, int NT, bool VEC>
+__device__ __forceinline__ void load_k_major(double* dst, const double* __restrict__ src,
+                                             long long ld, int mn0, int k0, int mn_max,
+                                             int k_max) {
+  if (VEC) {
+    constexpr int PAIRS = BK / 2;
+#pragma unroll
+    for (int idx = threadIdx.x; idx < BMN * PAIRS; idx += NT) {
+      const int kk = (idx % PAIRS) * 2, mn = idx / PAIRS;
+      const int gm = mn0 + mn, gk = k0 + kk;
+      int valid = (gm < mn_max) ? max(0, min(2, k_max - gk)) : 0;
+      const double* g = valid ? (src + gk + (long long)gm * ld) : src;
+      cp_async16(dst + mn * KPAD + kk, g, valid * 8);
+    }
+  } else {
+#pragma unroll
+    for (int idx = threadIdx.x; idx < BMN * BK; idx += NT) {
+      const int kk = idx % BK, mn = idx / BK;
+      const int gm = mn0 + mn, gk = k0 + kk;
+      const bool valid = (gk < k_max) && (gm < mn_max);
+      const double* g = valid ? (src + gk + (long long)gm * ld) : src;
+      cp_async8(dst + mn * KPAD + kk, g, valid ? 8 : 0);
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC>
+__global__ void __launch_bounds__(WM* WN * 32)
+    dgemm_kernel(const GemmProb single, const GemmProb* __restrict__ probs, int splits,
+                 double* __restrict__ ws) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int WTM = BM / WM, WTN = BN / WN;  // warp tile
+  constexpr int MT = WTM / 8, NTL = WTN / 8;   // 8x8 DMMA tiles per warp
+  constexpr int SA = BM + 4, SB = BN + 4;
+  constexpr int A_STAGE = TileSize<BM>::max, B_STAGE = TileSize<BN>::max;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+
+  const GemmProb pr = probs ? probs[blockIdx.z] : single;
+  const int tiles_m = (pr.m + BM - 1) / BM, tiles_n = (pr.n + BN - 1) / BN;
+  if ((int)blockIdx.x >= tiles_m * tiles_n) return;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  const int m0 = tm * BM, n0 = tn * BN;
+  if (pr.lower && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
+
+  // split-K range (multiples of BK)
+  int kbeg = 0, kend = pr.k;
+  if (splits > 1) {
+    const int ktiles = (pr.k + BK - 1) / BK;
+    const int per = (ktiles + splits - 1) / splits;
+    kbeg = min(pr.k, (int)blockIdx.y * per * BK);
+    kend = min(pr.k, kbeg + per * BK);
+  }
+  const int KT = (kend - kbeg + BK - 1) / BK;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % WM) * WTM, wn0 = (warp / WM) * WTN;
+
+  double acc[MT][NTL][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_stage = [&](int stage, int kt) {
+    const int k0 = kbeg + kt * BK;
+    double* a = As + stage * A_STAGE;
+    double* b = Bs + stage * B_STAGE;
+    if (TA)
+      load_k_major<BM, NT, VEC>(a, pr.A, pr.lda, m0, k0, pr.m, kend);
+    else
+      load_mn_major<BM, NT, VEC>(a, pr.A, pr.lda, m0, k0, pr.m, kend);
+    if (TB)
+      load_mn_major<BN, NT, VEC>(b, pr.B, pr.ldb, n0, k0, pr.n, kend);
+    else
+      load_k_major<BN, NT, VEC>(b, pr.B, pr.ldb, n0, k0, pr.n, kend);
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < KT) load_stage(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const double* a = As + (kt % STAGES) * A_STAGE;
+    const double* b = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      double af[MT], bf[NTL];
+      const int kk = ks * 4 + t;
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int row = wm0 + i * 8 + g;
+        af[i] = TA ? a[row * KPAD + kk] : a[kk * SA + row];
+      }
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) {
+        const int col = wn0 + j * 8 + g;
+        bf[j] = TB ? b[kk * SB + col] : b[col * KPAD + kk];
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue
+  double* C = pr.C;
+  long long ldc = pr.ldc;
+  double alpha = pr.alpha, beta = pr.beta;
+  if (splits > 1) {
+    C = ws + (size_t)blockIdx.y * (size_t)pr.m * (size_t)pr.n;
+    ldc = pr.m;
+    alpha = 1.0;
+    beta = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int row = m0 + wm0 + i * 8 + g;
+    if (row >= pr.m) continue;
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + wn0 + j * 8 + 2 * t + e;
+        if (col < pr.n) {
+          double* c = C + row + (long long)col * ldc;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * (*c);
+          *c = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(GemmProb pr, int splits, const double* __restrict__ ws) {
+  const long long total = (long long)pr.m * pr.n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx % pr.m), col = (int)(idx / pr.m);
+    double s = 0.0;
+    for (int sp = 0; sp < splits; ++sp) s += ws[(size_t)sp * total + idx];
+    double* c = pr.C + row + (long long)col * pr.ldc;
+    double v = pr.alpha * s;
+    if (pr.beta != 0.0) v += pr.beta * (*c);
+    *c = v;
+  }
+}
+
+template <int BM, int BN, int WM, int WN>
+static size_t smem_bytes() {
+  return (size_t)STAGES * (TileSize<BM>::max + TileSize<BN>::max) * sizeof(double);
+}
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC>
+static int launch_one(bk_ctx* ctx, const GemmProb& single, const GemmProb* dprobs, int nprob,
+                      int max_tiles, int splits, double* ws) {
+  auto kern = dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC>;
+  const size_t smem = smem_bytes<BM, BN, WM, WN>();
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(max_tiles, splits, nprob);
+  kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(single, dprobs, splits, ws);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  return BK_OK;
+}
+
+template <int BM, int BN, int WM, int WN>
+static int dispatch(bk_ctx* ctx, bool ta, bool tb, bool vec, const GemmProb& single,
+                    const GemmProb* dprobs, int nprob, int max_tiles, int splits, double* ws) {
+#define BK_GEMM_CASE(TA_, TB_, V_)                                                              \
+  if (ta == TA_ && tb == TB_ && vec == V_)                                                      \
+    return launch_one<BM, BN, WM, WN, TA_, TB_, V_>(ctx, single, dprobs, nprob, max_tiles, splits, \
+                                                     ws);
+  BK_GEMM_CASE(false, false, false)
+  BK_GEMM_CASE(false, false, true)
+  BK_GEMM_CASE(false, true, false)
+  BK_GEMM_CASE(false, true, true)
+  BK_GEMM_CASE(true, false, false)
+  BK_GEMM_CASE(true, false, true)
+  BK_GEMM_CASE(true, true, false)
+  BK_GEMM_CASE(true, true, true)
+#undef BK_GEMM_CASE
+  return BK_ERR_ARG;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+bool gemm_operands_vec_ok(const void* A, long long lda, const void* B, long long ldb) {
+  return aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
+}
+
+int gemm_batched(bk_ctx* ctx, bool ta, bool tb, const GemmProb* dprobs, int nprob, int max_m,
+                 int max_n, bool vec) {
+  if (nprob <= 0 || max_m <= 0 || max_n <= 0) return BK_OK;
+  GemmProb none{};
+  if (max_n <= 32) {
+    const int tiles = (int)(ceil_div(max_m, 128) * ceil_div(max_n, 32));
+    return dispatch<128, 32, 8, 1>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
+  } else if (max_m <= 64 || max_n <= 64) {
+    const int tiles = (int)(ceil_div(max_m, 64) * ceil_div(max_n, 64));
+    return dispatch<64, 64, 2, 4>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
+  }
+  const int tiles = (int)(ceil_div(max_m, 128) * ceil_div(max_n, 128));
+  return dispatch<128, 128, 2, 4>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
+}
+
+int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
+         long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
+         bool lower) {
+  if (m <= 0 || n <= 0) return BK_OK;
+  GemmProb p;
+  p.A = A;
+  p.B = B;
+  p.C = C;
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  p.lda = lda;
+  p.ldb = ldb;
+  p.ldc = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.lower = lower ? 1 : 0;
+  const bool vec = gemm_operands_vec_ok(A, lda, B, ldb);
+
+  int bm, bn;
+  if (n <= 32) {
+    bm = 128;
+    bn = 32;
+  } else if (m <= 64 || n <= 64) {
+    bm = 64;
+    bn = 64;
+  } else {
+    bm = 128;
+    bn = 128;
+  }
+  const int tiles = (int)(ceil_div(m, bm) * ceil_div(n, bn));
+  // deterministic split-K when the tile grid cannot fill the machine and k is long
+  int splits = 1;
+  if (!lower && tiles < ctx->sm_count && k >= 1024) {
+    splits = (int)std::min<int64_t>(ceil_div(2 * ctx->sm_count, tiles), k / 256);
+    splits = std::max(1, std::min(splits, 64));
+  }
+  double* ws = nullptr;
+  if (splits > 1) {
+    BK_TRY(ctx->gemm_ws.ensure((size_t)splits * (size_t)m * (size_t)n));
+    ws = ctx->gemm_ws.p;
+  }
+  int rc;
+  if (bn == 32)
+    rc = dispatch<128, 32, 8, 1>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
+  else if (bm == 64)
+    rc = dispatch<64, 64, 2, 4>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
+  else
+    rc = dispatch<128, 128, 2, 4>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
+  BK_TRY(rc);
+  if (splits > 1) {
+    const long long total = (long long)m * n;
+    const int blocks = (int)std::min<long long>(ceil_div(total, 256), 4 * ctx->sm_count);
+    splitk_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(p, splits, ws);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(cudaGetLastError());
+  }
+  return BK_OK;
+}
+
+}  // namespace bk

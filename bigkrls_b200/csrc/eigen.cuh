@@ -1,0 +1,55 @@
+// Symmetric eigensolver internals (device pointers, context stream).
+#pragma once
+#include "common.cuh"
+
+namespace bk {
+
+// A (n x n, lower triangle referenced and overwritten) -> d[n], e[n-1], tau[n-1] (device);
+// reflectors stored LAPACK-style below the first sub-diagonal of A.
+int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double* e, double* tau,
+                int nb);
+
+struct StedcStats {
+  int levels = 0;
+  long long merge_flops = 0;   // flops of the merge GEMMs actually executed
+  int top_n = 0, top_k = 0;    // size and non-deflated count of the root merge
+};
+
+// Divide & conquer on the tridiagonal (d, e: HOST arrays, n and n-1).  On return
+// evals_host[n] ASCENDING.  Eigenvectors: among the max_want largest eigenvalues, those
+// with value >= rel_thresh * largest are kept (*n_want of them, the reference's `lastkeeper`
+// rule applied to the leading max_want values); Z (n x *n_want, ld = ldz, device, capacity
+// n x max_want) gets their eigenvectors, column c <-> the (c+1)-th largest.
+int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double* evals_host,
+          int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
+          StedcStats* stats);
+
+// Z (n x k) <- Q Z with Q = H_0 H_1 ... H_{n-2} the reflectors left in A by sytrd_lower.
+int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double* tau, double* Z,
+                long long ldz, int k);
+
+struct EigenTimes {
+  double tridiag = 0, dc = 0, backtransform = 0;
+  StedcStats dc_stats;
+};
+
+// Full path: K (n x n symmetric, device, preserved) -> evals_host[n] DESCENDING and the
+// eigenvectors selected as in stedc().  `work` is an n x n scratch (destroyed).
+int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work, long long ldw,
+               double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z,
+               long long ldz, EigenTimes* times);
+
+// Pure host logic of one D&C merge, exported for the CPU unit tests (tests/test_host_logic.py)
+struct MergePlan {
+  int K = 0;
+  double rho = 0;
+  std::vector<double> dlam, w;      // non-deflated poles (ascending) and weights
+  std::vector<int> nd_cols, nd_type;
+  std::vector<int> defl_cols;
+  std::vector<double> defl_vals;
+  struct Rot { int pj, nj; double c, s; };
+  std::vector<Rot> rots;
+};
+void host_deflate(const double* d, const double* z, int n, int n1, double beta, MergePlan* plan);
+
+}  // namespace bk

@@ -1,0 +1,704 @@
+// Fused, device-resident bigKRLS fit: the five stages of reference R/bigKRLS.R:262-329 behind
+// one C call, with X, K, Q, Lambda, c never leaving HBM between stages.
+//
+//   1/5 kernel            gauss_kernel.cu                       (src/gauss_kernel.cpp)
+//   2/5 eigen             sytrd.cu + stedc.cu + ormtr.cu        (src/eigen.cpp, bEigen R:173-199)
+//   3/5 lambda            golden section on the host, bit-for-bit the arithmetic of
+//                         R/bigKRLS_Rcpp_functions.R:5-82, with the LOO loss of up to 15
+//                         speculative candidates per pass over Q (loo.cu)
+//   4/5 coefficients      c (loo.cu), yhat = K c, sigma^2, vcov(c) = s2 Q (L+lam)^-2 Q',
+//                         vcov(yhat) = s2 Q (L/(L+lam))^2 Q'    (R/bigKRLS.R:286-307)
+//   5/5 marginal effects  one tall-skinny pass K [1 c X X.c], epilogue, spectral variances
+//                         (src/bigderiv_v3.cpp)
+//
+// Multi-GPU (one process per GPU): N x N matrices are partitioned by COLUMN BLOCKS - for the
+// symmetric K, V this is the transposed row panel, and it is contiguous in column-major
+// storage so blocks can be all-gathered in place.  The eigensolver runs on rank 0 and Q is
+// broadcast.  All collectives go through the bk_comm callbacks (NCCL via torch.distributed
+// in the Python host).
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <cstring>
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "eigen.cuh"
+#include "kernels.cuh"
+
+using namespace bk;
+
+struct bk_fit {
+  bk_ctx* ctx = nullptr;
+  int n = 0, p = 0, neig = 0, k = 0, pd = 0;
+  int rank = 0, world = 1;
+  int c0 = 0, c1 = 0;  // owned column block of the N x N fields
+  bk_fit_opts opts;
+  std::vector<int> which;      // derivative columns (0-based)
+  std::vector<double> evals;   // all neig eigenvalues, descending (host)
+  double lambda = 0, Le = 0, sigmasq = 0, neffective = 0;
+  int n_probes = 0, n_passes = 0;
+  bk_fit_info info;
+  DevBuf<double> X, y, K, Q, ev, w, c, yhat, sig2, Vc, Vf, D, var, binfo;
+  bool have_vcov = false, have_vf = false, have_deriv = false;
+};
+
+namespace {
+
+#define COMM_CALL(expr, what)                                   \
+  do {                                                          \
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));                \
+    if ((expr) != 0) {                                          \
+      set_error("communicator callback failed: %s", what);      \
+      return BK_ERR_COMM;                                       \
+    }                                                           \
+  } while (0)
+
+// ---- lambda bounds: R/bigKRLS_Rcpp_functions.R:16-36 (all Neig eigenvalues; R's sum()
+// accumulates in long double) -------------------------------------------------------------------
+long double ratio_sum(const std::vector<double>& ev, double x) {
+  long double s = 0.0L;
+  for (double e : ev) s += (long double)(e / (e + x));
+  return s;
+}
+
+int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
+  if (*U <= 0.0) {
+    double u = (double)n;
+    while ((double)ratio_sum(ev, u) < 1.0) {
+      u -= 1.0;
+      if (u <= 0.0) {
+        set_error("lambda search: upper bound loop did not terminate (degenerate spectrum)");
+        return BK_ERR_NUMERIC;
+      }
+    }
+    *U = u;
+  }
+  if (*L <= 0.0) {
+    double l = 2.220446049250313e-16;  // .Machine$double.eps (R/bigKRLS_Rcpp_functions.R:28)
+    const double emax = *std::max_element(ev.begin(), ev.end());
+    int q = 0;
+    double best = INFINITY;
+    for (size_t i = 0; i < ev.size(); ++i) {
+      const double v = std::fabs(ev[i] - emax / 1000.0);
+      if (v < best) {
+        best = v;
+        q = (int)i + 1;  // which.min: 1-based, first minimum
+      }
+    }
+    int guard = 0;
+    while ((double)ratio_sum(ev, l) > (double)q) {
+      l += 0.05;
+      if (++guard > 100000000) {
+        set_error("lambda search: lower bound loop did not terminate");
+        return BK_ERR_NUMERIC;
+      }
+    }
+    *L = l;
+  }
+  return BK_OK;
+}
+
+struct GState {
+  double L, U, X1, X2;
+};
+const double GOLD = 0.381966;
+
+// one golden-section step given the outcome of `S1 < S2` (R/bigKRLS_Rcpp_functions.R:56-69);
+// returns the newly required evaluation point.
+double gs_step(GState& s, bool s1_less) {
+  if (s1_less) {
+    s.U = s.X2;
+    s.X2 = s.X1;
+    s.X1 = s.L + GOLD * (s.U - s.L);
+    return s.X1;
+  }
+  s.L = s.X1;
+  s.X1 = s.X2;
+  s.X2 = s.U - GOLD * (s.U - s.L);
+  return s.X2;
+}
+
+struct LooEvaluator {
+  bk_ctx* ctx;
+  const bk_comm* comm;
+  const double* Q;  // row panel base (already offset to the first owned row)
+  long long ldq;
+  int n_rows, k;
+  const double* ev;  // device, first k eigenvalues
+  const double* z;   // device, Q'y
+  double* Le_dev;    // device, 16 doubles
+  int batch;
+  std::map<uint64_t, double> cache;
+  int passes = 0;
+
+  static uint64_t key(double v) {
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return u;
+  }
+  bool has(double lam) const { return cache.count(key(lam)) != 0; }
+
+  int run(const std::vector<double>& lams) {
+    double host[16];
+    BK_TRY(loo_batch(ctx, Q, ldq, n_rows, k, ev, z, lams.data(), (int)lams.size(), Le_dev, nullptr));
+    if (comm && comm->world > 1) COMM_CALL(comm->allreduce_sum(comm->user, Le_dev, 16), "allreduce(Le)");
+    BK_CUDA(cudaMemcpyAsync(host, Le_dev, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < lams.size(); ++i) cache[key(lams[i])] = host[i];
+    ++passes;
+    return BK_OK;
+  }
+
+  // Le(lam); on a miss evaluates lam together with the speculative continuation of the search
+  // tree rooted at `st` (breadth first, so the shallow levels are kept when the batch is full).
+  int get(double lam, const GState& st, const std::vector<double>& also, double* out) {
+    if (!has(lam)) {
+      std::vector<double> lams;
+      auto push = [&](double v) {
+        if ((int)lams.size() >= batch || has(v)) return;
+        for (double x : lams)
+          if (key(x) == key(v)) return;
+        lams.push_back(v);
+      };
+      push(lam);
+      for (double v : also) push(v);
+      std::vector<GState> frontier{st};
+      while ((int)lams.size() < batch && !frontier.empty() && frontier.size() < 64) {
+        std::vector<GState> next;
+        for (const GState& s : frontier) {
+          for (int o = 0; o < 2; ++o) {
+            GState c = s;
+            push(gs_step(c, o == 0));
+            next.push_back(c);
+          }
+        }
+        frontier.swap(next);
+      }
+      BK_TRY(run(lams));
+    }
+    *out = cache[key(lam)];
+    return BK_OK;
+  }
+};
+
+int lambda_search(LooEvaluator& ev, double L, double U, double tol, double* lam_out, int* probes) {
+  GState s;
+  s.L = L;
+  s.U = U;
+  s.X1 = L + GOLD * (U - L);  // :38
+  s.X2 = U - GOLD * (U - L);  // :39
+  double S1, S2;
+  BK_TRY(ev.get(s.X1, s, {s.X2}, &S1));
+  BK_TRY(ev.get(s.X2, s, {}, &S2));
+  int np = 2;
+  while (std::fabs(S1 - S2) > tol) {  // :54
+    if (!std::isfinite(S1) || !std::isfinite(S2)) {
+      set_error("lambda search: leave-one-out loss is not finite");
+      return BK_ERR_NUMERIC;
+    }
+    if (S1 < S2) {
+      const double x = gs_step(s, true);
+      S2 = S1;
+      BK_TRY(ev.get(x, s, {}, &S1));
+    } else {
+      const double x = gs_step(s, false);
+      S1 = S2;
+      BK_TRY(ev.get(x, s, {}, &S2));
+    }
+    if (++np > 10000) {
+      set_error("lambda search: no convergence after 10000 probes");
+      return BK_ERR_NUMERIC;
+    }
+  }
+  *lam_out = (S1 < S2) ? s.X1 : s.X2;  // :71
+  *probes = np;
+  return BK_OK;
+}
+
+int run_fit(bk_fit* f, const bk_comm* comm) {
+  bk_ctx* ctx = f->ctx;
+  const int n = f->n, p = f->p;
+  const bk_fit_opts& o = f->opts;
+  const long long ld = n;
+  const bool multi = comm && comm->world > 1;
+  Timer tm, total;
+  BK_TRY(tm.init(ctx->stream));
+  BK_TRY(total.init(ctx->stream));
+  total.start();
+  memset(&f->info, 0, sizeof(f->info));
+
+  // ---- 1/5 kernel -------------------------------------------------------------------------
+  tm.start();
+  BK_TRY(f->K.alloc((size_t)n * n));
+  if (!multi) {
+    BK_TRY(gauss_kernel_sym(ctx, f->X.p, ld, n, p, o.sigma, f->K.p, ld));
+  } else {
+    // own column block K[:, c0:c1] = kernel(X, X[c0:c1, :]) then in-place all-gather
+    BK_TRY(gauss_kernel_rect(ctx, f->X.p, ld, n, f->X.p + f->c0, ld, f->c1 - f->c0, p, o.sigma,
+                             f->K.p + (long long)f->c0 * ld, ld));
+    std::vector<int64_t> counts(comm->world), displs(comm->world);
+    for (int r = 0; r < comm->world; ++r) {
+      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
+      counts[r] = (b - a) * n;
+      displs[r] = a * n;
+    }
+    COMM_CALL(comm->allgatherv(comm->user, f->K.p, counts.data(), displs.data()), "allgatherv(K)");
+  }
+  f->info.t_kernel = tm.stop();
+
+  // ---- 2/5 eigen ----------------------------------------------------------------------------
+  tm.start();
+  f->evals.assign(f->neig, 0.0);
+  int k = 0;
+  {
+    DevBuf<double> Zfull;
+    BK_TRY(Zfull.alloc((size_t)n * f->neig));
+    if (!multi || comm->rank == 0) {
+      DevBuf<double> work;
+      BK_TRY(work.alloc((size_t)n * n));
+      std::vector<double> ev(n);
+      EigenTimes et;
+      BK_TRY(eigen_full(ctx, f->K.p, ld, n, work.p, ld, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p,
+                        ld, &et));
+      for (int i = 0; i < f->neig; ++i) f->evals[i] = ev[i];
+      f->info.t_tridiag = et.tridiag;
+      f->info.t_dc = et.dc;
+      f->info.t_backtransform = et.backtransform;
+    }
+    BK_TRY(f->ev.alloc(f->neig + 1));
+    if (multi) {
+      // broadcast [k, evals] then Q[:, :k]
+      std::vector<double> pack(f->neig + 1);
+      pack[0] = (double)k;
+      for (int i = 0; i < f->neig; ++i) pack[1 + i] = f->evals[i];
+      BK_CUDA(cudaMemcpyAsync(f->ev.p, pack.data(), sizeof(double) * (f->neig + 1),
+                              cudaMemcpyHostToDevice, ctx->stream));
+      COMM_CALL(comm->broadcast(comm->user, f->ev.p, f->neig + 1, 0), "broadcast(evals)");
+      BK_CUDA(cudaMemcpyAsync(pack.data(), f->ev.p, sizeof(double) * (f->neig + 1),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+      k = (int)pack[0];
+      for (int i = 0; i < f->neig; ++i) f->evals[i] = pack[1 + i];
+      COMM_CALL(comm->broadcast(comm->user, Zfull.p, (int64_t)n * k, 0), "broadcast(Q)");
+    }
+    BK_REQUIRE(k >= 1, "eigen: no eigenpair retained");
+    BK_CUDA(cudaMemcpyAsync(f->ev.p, f->evals.data(), sizeof(double) * f->neig, cudaMemcpyHostToDevice,
+                            ctx->stream));
+    // keep a compact n x k copy when truncation dropped most columns
+    if ((size_t)k * 2 < (size_t)f->neig) {
+      BK_TRY(f->Q.alloc((size_t)n * k));
+      BK_CUDA(cudaMemcpyAsync(f->Q.p, Zfull.p, sizeof(double) * (size_t)n * k, cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+      std::swap(f->Q.p, Zfull.p);
+      std::swap(f->Q.n, Zfull.n);
+    }
+  }
+  f->k = k;
+  for (double e : f->evals)
+    if (!std::isfinite(e)) {
+      // R/bigKRLS_Rcpp_functions.R:8-9
+      set_error("Missing eigenvalues prevent bigKRLS from obtaining the regularization parameter "
+                "lambda. Check for repeated observations (or other perfect linear combinations in X).");
+      return BK_ERR_NUMERIC;
+    }
+  f->info.t_eigen = tm.stop();
+
+  // ---- 3/5 lambda ---------------------------------------------------------------------------
+  tm.start();
+  DevBuf<double> z, Le_dev;
+  BK_TRY(z.alloc(k));
+  BK_TRY(Le_dev.alloc(16));
+  BK_TRY(gemm(ctx, true, false, k, 1, n, 1.0, f->Q.p, ld, f->y.p, ld, 0.0, z.p, k));
+  const int nloc = f->c1 - f->c0;
+  double lam = o.lambda;
+  if (!(lam > 0.0)) {
+    double L = o.L, U = o.U;
+    BK_TRY(lambda_bounds(f->evals, n, &L, &U));
+    const double tol = (o.tol > 0.0) ? o.tol : 1e-3 * n;  // R:10-12 (bigKRLS() never forwards tol)
+    LooEvaluator le;
+    le.ctx = ctx;
+    le.comm = comm;
+    le.Q = f->Q.p + f->c0;
+    le.ldq = ld;
+    le.n_rows = nloc;
+    le.k = k;
+    le.ev = f->ev.p;
+    le.z = z.p;
+    le.Le_dev = Le_dev.p;
+    le.batch = std::max(1, std::min(15, o.loo_batch > 0 ? o.loo_batch : 7));
+    BK_TRY(lambda_search(le, L, U, tol, &lam, &f->n_probes));
+    f->n_passes = le.passes;
+  }
+  f->lambda = lam;
+  {
+    long double s = 0.0L;  // R/bigKRLS.R:280 (all Neig eigenvalues)
+    for (double e : f->evals) s += (long double)(e / (e + lam));
+    f->neffective = (double)((long double)n - s);
+  }
+  f->info.t_lambda = tm.stop();
+
+  // ---- 4/5 coefficients, fitted values ----------------------------------------------------------
+  tm.start();
+  BK_TRY(f->c.alloc(n));
+  BK_TRY(loo_batch(ctx, f->Q.p + f->c0, ld, nloc, k, f->ev.p, z.p, &lam, 1, Le_dev.p, f->c.p + f->c0));
+  if (multi) {
+    COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
+    std::vector<int64_t> counts(comm->world), displs(comm->world);
+    for (int r = 0; r < comm->world; ++r) {
+      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
+      counts[r] = b - a;
+      displs[r] = a;
+    }
+    COMM_CALL(comm->allgatherv(comm->user, f->c.p, counts.data(), displs.data()), "allgatherv(coeffs)");
+  }
+  BK_CUDA(cudaMemcpyAsync(&f->Le, Le_dev.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+
+  // K-pass: KW = K [1 c {x_j|b_j} {x_j c|b_j c}] ; column 1 is yhat = K c  (R/bigKRLS.R:291)
+  const int pd = o.derivative ? f->pd : 0;
+  const int mw = 2 * pd + 2;
+  DevBuf<double> Xd, W, KW;
+  BK_TRY(f->binfo.alloc(3 * std::max(1, pd)));
+  if (pd > 0) {
+    BK_TRY(Xd.alloc((size_t)n * pd));
+    std::vector<int> wh(f->which);
+    DevBuf<int> whd;
+    BK_TRY(whd.alloc(pd));
+    BK_CUDA(cudaMemcpyAsync(whd.p, wh.data(), sizeof(int) * pd, cudaMemcpyHostToDevice, ctx->stream));
+    BK_TRY(gather_columns(ctx, f->X.p, ld, n, pd, whd.p, Xd.p, ld));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_TRY(column_binary_info(ctx, Xd.p, ld, n, pd, f->binfo.p));
+  }
+  BK_TRY(W.alloc((size_t)n * mw));
+  BK_TRY(KW.alloc((size_t)n * mw));
+  BK_TRY(build_kpass_rhs(ctx, Xd.p, ld, n, pd, f->c.p, f->binfo.p, W.p, ld));
+  // rows [c0, c1) of K W = (K[:, c0:c1])' W     (K symmetric)
+  if (!multi)
+    BK_TRY(gemm(ctx, false, false, n, mw, n, 1.0, f->K.p, ld, W.p, ld, 0.0, KW.p, ld));
+  else
+    BK_TRY(gemm(ctx, true, false, nloc, mw, n, 1.0, f->K.p + (long long)f->c0 * ld, ld, W.p, ld, 0.0,
+                KW.p + f->c0, ld));
+  BK_TRY(f->yhat.alloc(n));
+  BK_TRY(copy_matrix(ctx, KW.p + f->c0 + ld, ld, nloc, 1, 1.0, f->yhat.p + f->c0, ld));
+  if (multi) {
+    std::vector<int64_t> counts(comm->world), displs(comm->world);
+    for (int r = 0; r < comm->world; ++r) {
+      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
+      counts[r] = b - a;
+      displs[r] = a;
+    }
+    COMM_CALL(comm->allgatherv(comm->user, f->yhat.p, counts.data(), displs.data()), "allgatherv(yhat)");
+  }
+  BK_TRY(f->sig2.alloc(1));
+  BK_TRY(residual_sigmasq(ctx, f->y.p, f->yhat.p, n, f->sig2.p));  // R/bigKRLS.R:294
+  f->info.t_coef = tm.stop();
+
+  // ---- vcov(c), vcov(yhat) in y_sd^2 units (R/bigKRLS.R:299-307, 439, 446) ----------------------------
+  tm.start();
+  DevBuf<double> w2;
+  BK_TRY(w2.alloc(k));
+  BK_TRY(spectral_weights(ctx, f->ev.p, k, lam, 1, w2.p));
+  if (o.vcov) {
+    const double ys2 = o.y_sd * o.y_sd;
+    DevBuf<double> M;
+    BK_TRY(M.alloc((size_t)n * k));
+    BK_TRY(f->Vc.alloc((size_t)n * nloc));
+    // m = Q diag(sigmasq (ev+lam)^-2)   (bMultDiag, R:299);  vcovmatc = m Q' (bTCrossProd, R:301)
+    BK_TRY(col_scale(ctx, f->Q.p, ld, n, k, w2.p, f->sig2.p, M.p, ld));
+    if (!multi) {
+      BK_TRY(gemm(ctx, false, true, n, n, k, ys2, M.p, ld, f->Q.p, ld, 0.0, f->Vc.p, ld, true));
+      BK_TRY(symmetrize_from_lower(ctx, f->Vc.p, ld, n));
+    } else {
+      BK_TRY(gemm(ctx, false, true, n, nloc, k, ys2, M.p, ld, f->Q.p + f->c0, ld, 0.0, f->Vc.p, ld));
+    }
+    f->have_vcov = true;
+    if (o.keep_vcov_fitted) {
+      // K'(V K) = sigmasq Q diag((ev/(ev+lam))^2) Q'  for exact eigenpairs of K (R:307)
+      DevBuf<double> w3;
+      BK_TRY(w3.alloc(k));
+      BK_TRY(spectral_weights(ctx, f->ev.p, k, lam, 2, w3.p));
+      BK_TRY(col_scale(ctx, f->Q.p, ld, n, k, w3.p, f->sig2.p, M.p, ld));
+      BK_TRY(f->Vf.alloc((size_t)n * nloc));
+      if (!multi) {
+        BK_TRY(gemm(ctx, false, true, n, n, k, ys2, M.p, ld, f->Q.p, ld, 0.0, f->Vf.p, ld, true));
+        BK_TRY(symmetrize_from_lower(ctx, f->Vf.p, ld, n));
+      } else {
+        BK_TRY(gemm(ctx, false, true, n, nloc, k, ys2, M.p, ld, f->Q.p + f->c0, ld, 0.0, f->Vf.p, ld));
+      }
+      f->have_vf = true;
+    }
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  f->info.t_vcov = tm.stop();
+
+  // ---- 5/5 marginal effects ------------------------------------------------------------------------
+  tm.start();
+  if (pd > 0) {
+    DevBuf<double> R, G;
+    BK_TRY(f->D.alloc((size_t)n * pd));
+    BK_TRY(R.alloc((size_t)n * pd));
+    BK_TRY(G.alloc((size_t)k * pd));
+    BK_TRY(f->var.alloc(pd));
+    BK_TRY(deriv_epilogue(ctx, Xd.p + f->c0, ld, nloc, pd, KW.p + f->c0, ld, f->binfo.p, o.sigma,
+                          f->D.p + f->c0, ld, R.p + f->c0, ld));
+    // G = Q' R (k x pd); r'V r = sigmasq * sum_i w2_i G_i^2
+    BK_TRY(gemm(ctx, true, false, k, pd, nloc, 1.0, f->Q.p + f->c0, ld, R.p + f->c0, ld, 0.0, G.p, k));
+    if (multi) {
+      COMM_CALL(comm->allreduce_sum(comm->user, G.p, (int64_t)k * pd), "allreduce(Q'R)");
+      // derivatives: gather row panels (n x pd is column-major, so go through a packed buffer)
+      DevBuf<double> pack;
+      BK_TRY(pack.alloc((size_t)n * pd));
+      std::vector<int64_t> counts(comm->world), displs(comm->world);
+      for (int r = 0; r < comm->world; ++r) {
+        const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
+        counts[r] = (b - a) * pd;
+        displs[r] = a * pd;
+      }
+      BK_TRY(copy_matrix(ctx, f->D.p + f->c0, ld, nloc, pd, 1.0, pack.p + displs[comm->rank], nloc));
+      COMM_CALL(comm->allgatherv(comm->user, pack.p, counts.data(), displs.data()), "allgatherv(D)");
+      for (int r = 0; r < comm->world; ++r) {
+        const int a = (int)((int64_t)n * r / comm->world), b = (int)((int64_t)n * (r + 1) / comm->world);
+        BK_TRY(copy_matrix(ctx, pack.p + displs[r], b - a, b - a, pd, 1.0, f->D.p + a, ld));
+      }
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    BK_TRY(deriv_variance_spectral(ctx, G.p, k, k, pd, w2.p, f->sig2.p, f->binfo.p, o.sigma, n, f->var.p));
+    f->have_deriv = true;
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  BK_CUDA(cudaMemcpyAsync(&f->sigmasq, f->sig2.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  f->info.t_deriv = tm.stop();
+  f->info.t_total = total.stop();
+
+  f->info.n = n;
+  f->info.p = p;
+  f->info.neig = f->neig;
+  f->info.lastkeeper = k;
+  f->info.n_deriv = pd;
+  f->info.lambda = f->lambda;
+  f->info.Le = f->Le;
+  f->info.sigmasq = f->sigmasq;
+  f->info.neffective = f->neffective;
+  f->info.n_probes = f->n_probes;
+  f->info.n_passes = f->n_passes;
+  return BK_OK;
+}
+
+int create_fit(bk_ctx* ctx, const double* Xs, const double* ys, bool on_device, int64_t n, int64_t p,
+               const bk_fit_opts* opts, const bk_comm* comm, bk_fit** out) {
+  BK_REQUIRE(ctx && Xs && ys && opts && out, "bk_fit_run: NULL argument");
+  BK_REQUIRE(n >= 2 && p >= 1 && n < 2147483647LL && p < 100000, "bk_fit_run: bad dimensions");
+  BK_REQUIRE(opts->sigma > 0.0, "bk_fit_run: sigma must be positive");
+  BK_REQUIRE(opts->eigtrunc >= 0.0 && opts->eigtrunc <= 1.0,
+             "eigtrunc must be between 0 (no truncation) and 1 (keep largest only).");  // R/bigKRLS.R:203
+  BK_REQUIRE(opts->neig >= 1 && opts->neig <= n, "bk_fit_run: neig must be in 1..n");
+  BK_REQUIRE(!(opts->derivative && !opts->vcov),
+             "vcov.est is needed to get derivatives (derivative==TRUE requires vcov.est=TRUE).");  // R:238
+  BK_REQUIRE(opts->y_sd > 0.0, "bk_fit_run: y_sd must be positive");
+  for (int i = 0; i < opts->n_which; ++i)
+    BK_REQUIRE(opts->which && opts->which[i] >= 0 && opts->which[i] < p,
+               "which.derivatives out of range");
+  if (comm && comm->world > 1)
+    BK_REQUIRE(comm->allreduce_sum && comm->allgatherv && comm->broadcast,
+               "bk_fit_run: communicator callbacks missing");
+  BK_CUDA(cudaSetDevice(ctx->device));
+  bk_fit* f = new bk_fit();
+  f->ctx = ctx;
+  f->n = (int)n;
+  f->p = (int)p;
+  f->neig = (int)opts->neig;
+  f->opts = *opts;
+  f->opts.which = nullptr;
+  if (opts->n_which > 0)
+    f->which.assign(opts->which, opts->which + opts->n_which);
+  else
+    for (int i = 0; i < (int)p; ++i) f->which.push_back(i);
+  f->pd = (int)f->which.size();
+  f->rank = comm ? comm->rank : 0;
+  f->world = comm ? comm->world : 1;
+  f->c0 = (int)((int64_t)n * f->rank / f->world);
+  f->c1 = (int)((int64_t)n * (f->rank + 1) / f->world);
+  int rc = f->X.alloc((size_t)n * p);
+  if (rc == BK_OK) rc = f->y.alloc(n);
+  if (rc == BK_OK) {
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMemcpyAsync(f->X.p, Xs, sizeof(double) * (size_t)n * p, kind, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->y.p, ys, sizeof(double) * (size_t)n, kind, ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("bk_fit_run: input copy failed: %s", cudaGetErrorString(e));
+      rc = BK_ERR_CUDA;
+    }
+  }
+  if (rc == BK_OK) rc = run_fit(f, comm);
+  if (rc != BK_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    delete f;
+    return rc;
+  }
+  *out = f;
+  return BK_OK;
+}
+
+int get_block(const bk_fit* f, const DevBuf<double>& buf, bool have, double* host, const char* what) {
+  BK_REQUIRE(f && host, "getter: NULL argument");
+  if (!have || !buf.p) {
+    set_error("%s was not computed for this fit", what);
+    return BK_ERR_STATE;
+  }
+  bk_ctx* ctx = f->ctx;
+  BK_CUDA(cudaSetDevice(ctx->device));
+  const size_t cnt = (size_t)f->n * (size_t)(f->c1 - f->c0);
+  // single-GPU fits hold the full matrix; multi-GPU fits hold only the owned block (Vc, Vf) or
+  // the full K (offset to the owned block)
+  BK_CUDA(cudaMemcpyAsync(host, buf.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+int get_vec(const bk_fit* f, const double* dev, size_t cnt, double* host) {
+  BK_REQUIRE(f && host && dev, "getter: NULL argument or field not computed");
+  bk_ctx* ctx = f->ctx;
+  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void bk_fit_default_opts(bk_fit_opts* o, int64_t n, int64_t p) {
+  memset(o, 0, sizeof(*o));
+  o->sigma = (double)p;                      // R/bigKRLS.R:230
+  o->eigtrunc = (n > 3000) ? 0.001 : 0.0;    // R/bigKRLS.R:195-201
+  o->neig = n;                               // R/bigKRLS.R:194
+  o->lambda = 0.0;
+  o->L = 0.0;
+  o->U = 0.0;
+  o->tol = 0.0;
+  o->derivative = 1;
+  o->vcov = 1;
+  o->n_which = 0;
+  o->which = nullptr;
+  o->y_sd = 1.0;
+  o->loo_batch = 7;
+  o->keep_vcov_fitted = 1;
+}
+
+int bk_fit_run(bk_ctx* ctx, const double* Xs, const double* ys, int64_t n, int64_t p,
+               const bk_fit_opts* opts, const bk_comm* comm, bk_fit** out) {
+  return create_fit(ctx, Xs, ys, false, n, p, opts, comm, out);
+}
+int bk_fit_run_device(bk_ctx* ctx, const double* dXs, const double* dys, int64_t n, int64_t p,
+                      const bk_fit_opts* opts, const bk_comm* comm, bk_fit** out) {
+  return create_fit(ctx, dXs, dys, true, n, p, opts, comm, out);
+}
+void bk_fit_free(bk_fit* f) {
+  if (!f) return;
+  cudaSetDevice(f->ctx->device);
+  cudaStreamSynchronize(f->ctx->stream);
+  delete f;
+}
+int bk_fit_get_info(const bk_fit* f, bk_fit_info* info) {
+  BK_REQUIRE(f && info, "bk_fit_get_info: NULL argument");
+  *info = f->info;
+  return BK_OK;
+}
+int bk_fit_col_range(const bk_fit* f, int64_t* c0, int64_t* c1) {
+  BK_REQUIRE(f && c0 && c1, "bk_fit_col_range: NULL argument");
+  *c0 = f->c0;
+  *c1 = f->c1;
+  return BK_OK;
+}
+int bk_fit_get_K(const bk_fit* f, double* host) {
+  BK_REQUIRE(f && host, "bk_fit_get_K: NULL argument");
+  return get_vec(f, f->K.p + (long long)f->c0 * f->n, (size_t)f->n * (size_t)(f->c1 - f->c0), host);
+}
+int bk_fit_get_eigenvalues(const bk_fit* f, double* host) {
+  BK_REQUIRE(f && host, "bk_fit_get_eigenvalues: NULL argument");
+  memcpy(host, f->evals.data(), sizeof(double) * f->evals.size());
+  return BK_OK;
+}
+int bk_fit_get_eigenvectors(const bk_fit* f, double* host) {
+  BK_REQUIRE(f, "bk_fit_get_eigenvectors: NULL argument");
+  return get_vec(f, f->Q.p, (size_t)f->n * f->k, host);
+}
+int bk_fit_get_coeffs(const bk_fit* f, double* host) {
+  BK_REQUIRE(f, "bk_fit_get_coeffs: NULL argument");
+  return get_vec(f, f->c.p, f->n, host);
+}
+int bk_fit_get_yfitted(const bk_fit* f, double* host) {
+  BK_REQUIRE(f, "bk_fit_get_yfitted: NULL argument");
+  return get_vec(f, f->yhat.p, f->n, host);
+}
+int bk_fit_get_vcov_c(const bk_fit* f, double* host) {
+  return get_block(f, f->Vc, f->have_vcov, host, "vcov.est.c");
+}
+int bk_fit_get_vcov_fitted(const bk_fit* f, double* host) {
+  return get_block(f, f->Vf, f->have_vf, host, "vcov.est.fitted");
+}
+int bk_fit_get_derivatives(const bk_fit* f, double* host) {
+  BK_REQUIRE(f, "bk_fit_get_derivatives: NULL argument");
+  if (!f->have_deriv) {
+    set_error("derivatives were not computed for this fit");
+    return BK_ERR_STATE;
+  }
+  return get_vec(f, f->D.p, (size_t)f->n * f->pd, host);
+}
+int bk_fit_get_var_avgderiv(const bk_fit* f, double* host) {
+  BK_REQUIRE(f, "bk_fit_get_var_avgderiv: NULL argument");
+  if (!f->have_deriv) {
+    set_error("derivatives were not computed for this fit");
+    return BK_ERR_STATE;
+  }
+  return get_vec(f, f->var.p, f->pd, host);
+}
+int bk_fit_get_binary(const bk_fit* f, int32_t* host) {
+  BK_REQUIRE(f && host, "bk_fit_get_binary: NULL argument");
+  if (!f->have_deriv) {
+    set_error("derivatives were not computed for this fit");
+    return BK_ERR_STATE;
+  }
+  std::vector<double> info(3 * f->pd);
+  BK_TRY(get_vec(f, f->binfo.p, 3 * f->pd, info.data()));
+  for (int j = 0; j < f->pd; ++j) host[j] = info[3 * j + 2] != 0.0;
+  return BK_OK;
+}
+
+int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred_std, double* Knew,
+                   double* se2) {
+  BK_REQUIRE(f && newXs && pred_std && m > 0 && m < 2147483647LL, "bk_fit_predict: bad arguments");
+  bk_ctx* ctx = f->ctx;
+  BK_CUDA(cudaSetDevice(ctx->device));
+  const int n = f->n, p = f->p, k = f->k, mi = (int)m;
+  DevBuf<double> dN, dK, dp;
+  BK_TRY(dN.alloc((size_t)m * p));
+  BK_TRY(dK.alloc((size_t)m * n));
+  BK_TRY(dp.alloc(m));
+  BK_CUDA(cudaMemcpyAsync(dN.p, newXs, sizeof(double) * (size_t)m * p, cudaMemcpyHostToDevice, ctx->stream));
+  // newdataK = bTempKernel(newdata, X, sigma)  (R/bigKRLS.R:599) ; ypred = newdataK %*% coeffs (:601)
+  BK_TRY(gauss_kernel_rect(ctx, dN.p, m, mi, f->X.p, n, n, p, f->opts.sigma, dK.p, m));
+  BK_TRY(gemm(ctx, false, false, mi, 1, n, 1.0, dK.p, m, f->c.p, n, 0.0, dp.p, m));
+  BK_CUDA(cudaMemcpyAsync(pred_std, dp.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  if (Knew)
+    BK_CUDA(cudaMemcpyAsync(Knew, dK.p, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (se2) {
+    // diag(Knew V Knew') with V = y_sd^2 sigmasq Q (ev+lam)^-2 Q'   (R/bigKRLS.R:608)
+    DevBuf<double> G, w2, s2;
+    BK_TRY(G.alloc((size_t)m * k));
+    BK_TRY(w2.alloc(k));
+    BK_TRY(s2.alloc(m));
+    BK_TRY(spectral_weights(ctx, f->ev.p, k, f->lambda, 1, w2.p));
+    BK_TRY(gemm(ctx, false, false, mi, k, n, 1.0, dK.p, m, f->Q.p, n, 0.0, G.p, m));
+    BK_TRY(row_quadform(ctx, G.p, m, mi, k, w2.p, f->sig2.p, f->opts.y_sd * f->opts.y_sd, s2.p));
+    BK_CUDA(cudaMemcpyAsync(se2, s2.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Leave-one-out loss of the lambda search, many candidate lambdas per pass over Q.
+//
+// Reference: src/solveforc.cpp:36-58 computes, for ONE lambda, row i of the lower triangle of
+// Ginv = Q diag(1/(ev+lambda)) Q' with N gemv's, then c = Ginv y, Le = sum (c_i/Ginv_ii)^2.
+// Closed form:  c = Q ((Q'y) o w),  diag(Ginv) = (Q o Q) w,  w = 1/(ev+lambda).
+// For L candidates this is the contraction  [Q , QoQ] x [ (z o W) ; W ]  (n x k x 2L) - one
+// read of Q (8nk bytes) serves every candidate, which is what makes the speculative
+// golden-section tree (fit.cu) cost one pass per 3 iterations.
+//
+// Kernel 1: thread = row, CTA = 256 rows x one k-slice; the 2L weight columns of the slice
+//           are staged in shared memory (broadcast reads), Q is read coalesced along rows,
+//           2L FP64 FMAs per loaded element.  Partials go to a [ksplit][2L][rows] buffer.
+// Kernel 2: fixed-order reduction over the k-slices, (c/d)^2, per-CTA partial sums.
+// Kernel 3: fixed-order sum of the CTA partials -> Le[L].  Deterministic (no atomics), so the
+//           discrete decisions of the golden section are reproducible run to run.
+// Roofline: HBM, 8 n k bytes per pass.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bk {
+
+struct LamPack {
+  double lam[16];
+};
+
+static constexpr int LOO_JC = 32;  // eigen-columns staged per chunk
+
+template <int L>
+__global__ void __launch_bounds__(256)
+    loo_partial_kernel(const double* __restrict__ Q, long long ldq, int n_rows, int k,
+                       const double* __restrict__ ev, const double* __restrict__ z, LamPack lp,
+                       int ksplit, double* __restrict__ part) {
+  __shared__ double g1[LOO_JC][L];  // z_j * w_jl
+  __shared__ double g2[LOO_JC][L];  // w_jl
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  const int per = (k + ksplit - 1) / ksplit;
+  const int kb = min(k, (int)blockIdx.y * per), ke = min(k, kb + per);
+  double c[L], d[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) c[l] = d[l] = 0.0;
+  const double* q = Q + (row < n_rows ? row : 0);
+
+  for (int j0 = kb; j0 < ke; j0 += LOO_JC) {
+    const int jc = min(LOO_JC, ke - j0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < LOO_JC * L; idx += 256) {
+      const int jj = idx / L, l = idx % L;
+      double w = 0.0, zz = 0.0;
+      if (jj < jc) {
+        w = 1.0 / (ev[j0 + jj] + lp.lam[l]);
+        zz = z[j0 + jj];
+      }
+      g1[jj][l] = zz * w;
+      g2[jj][l] = w;
+    }
+    __syncthreads();
+    if (row < n_rows) {
+#pragma unroll 4
+      for (int jj = 0; jj < jc; ++jj) {
+        const double v = q[(long long)(j0 + jj) * ldq];
+        const double v2 = v * v;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          c[l] = fma(v, g1[jj][l], c[l]);
+          d[l] = fma(v2, g2[jj][l], d[l]);
+        }
+      }
+    }
+  }
+  if (row < n_rows) {
+    double* o = part + (size_t)blockIdx.y * (2 * L) * (size_t)n_rows + row;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      o[(size_t)(2 * l) * n_rows] = c[l];
+      o[(size_t)(2 * l + 1) * n_rows] = d[l];
+    }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+    loo_finish_kernel(const double* __restrict__ part, int n_rows, int ksplit,
+                      double* __restrict__ blockpart, double* __restrict__ coeffs) {
+  __shared__ double red[32];
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  double e[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) e[l] = 0.0;
+  if (row < n_rows) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      double c = 0.0, d = 0.0;
+      for (int s = 0; s < ksplit; ++s) {
+        const double* o = part + (size_t)s * (2 * L) * (size_t)n_rows + row;
+        c += o[(size_t)(2 * l) * n_rows];
+        d += o[(size_t)(2 * l + 1) * n_rows];
+      }
+      const double r = c / d;  // src/solveforc.cpp:57
+      e[l] = r * r;
+      if (l == 0 && coeffs) coeffs[row] = c;
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const double s = block_sum(e[l], red);
+    if (threadIdx.x == 0) blockpart[(size_t)blockIdx.x * L + l] = s;
+  }
+}
+
+template <int L>
+__global__ void loo_final_kernel(const double* __restrict__ blockpart, int nblocks,
+                                 double* __restrict__ Le) {
+  const int l = threadIdx.x;
+  if (l >= L) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * L + l];
+  Le[l] = s;
+}
+
+template <int L>
+static int loo_run(bk_ctx* ctx, const double* Q, long long ldq, int n_rows, int k,
+                   const double* ev, const double* z, const LamPack& lp, double* Le_dev,
+                   double* coeffs) {
+  const int rb = (int)ceil_div(n_rows, 256);
+  int ksplit = (int)ceil_div(2LL * ctx->sm_count * 1024, (long long)rb * 256);
+  ksplit = std::max(1, std::min(ksplit, std::min(64, (k + 63) / 64)));
+  const size_t part_elems = (size_t)ksplit * 2 * L * (size_t)n_rows;
+  const size_t bp_elems = (size_t)rb * L;
+  BK_TRY(ctx->gemm_ws.ensure(part_elems + bp_elems));
+  double* part = ctx->gemm_ws.p;
+  double* bp = part + part_elems;
+  dim3 grid(rb, ksplit);
+  loo_partial_kernel<L><<<grid, 256, 0, ctx->stream>>>(Q, ldq, n_rows, k, ev, z, lp, ksplit, part);
+  BK_LAUNCHED(ctx);
+  loo_finish_kernel<L><<<rb, 256, 0, ctx->stream>>>(part, n_rows, ksplit, bp, coeffs);
+  BK_LAUNCHED(ctx);
+  loo_final_kernel<L><<<1, 32, 0, ctx->stream>>>(bp, rb, Le_dev);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  return BK_OK;
+}
+
+int loo_batch(bk_ctx* ctx, const double* Q, long long ldq, int n_rows, int k, const double* ev,
+              const double* z, const double* lambdas_host, int nlam, double* Le_dev,
+              double* coeffs) {
+  BK_REQUIRE(nlam >= 1 && nlam <= 16, "loo_batch: nlam must be in 1..16 (got %d)", nlam);
+  BK_REQUIRE(coeffs == nullptr || nlam == 1, "loo_batch: coefficients need a single lambda");
+  LamPack lp;
+  for (int i = 0; i < 16; ++i) lp.lam[i] = lambdas_host[std::min(i, nlam - 1)];
+  if (nlam == 1) return loo_run<1>(ctx, Q, ldq, n_rows, k, ev, z, lp, Le_dev, coeffs);
+  if (nlam == 2) return loo_run<2>(ctx, Q, ldq, n_rows, k, ev, z, lp, Le_dev, coeffs);
+  if (nlam <= 4) return loo_run<4>(ctx, Q, ldq, n_rows, k, ev, z, lp, Le_dev, coeffs);
+  if (nlam <= 8) return loo_run<8>(ctx, Q, ldq, n_rows, k, ev, z, lp, Le_dev, coeffs);
+  return loo_run<16>(ctx, Q, ldq, n_rows, k, ev, z, lp, Le_dev, coeffs);
+}
+
+}  // namespace bk

@@ -1,0 +1,133 @@
+// Back-transformation of the tridiagonal eigenvectors, Z <- Q Z with Q = H_0 H_1 ... H_{n-2}
+// the Householder reflectors left below the sub-diagonal by sytrd.cu (LAPACK dormtr role inside
+// dsyevd; reference src/eigen.cpp:24), plus the full-eigensolver driver.
+//
+// Blocked compact-WY form: for each block of ib reflectors (last block first)
+//     Z[j0+1:, :] -= V (T (V' Z[j0+1:, :]))        H_j0 ... H_{j0+ib-1} = I - V T V'
+// V is unpacked to an explicit unit-lower-trapezoidal panel so that all three products run
+// on the DMMA GEMM; T comes from S = V'V (split-K GEMM) and an ib-step triangular recurrence.
+// Only the k = lastkeeper columns that the fit will use are transformed: 4 n k ib flops per
+// block, 2 n^2 k in total.
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "eigen.cuh"
+#include "kernels.cuh"
+
+namespace bk {
+
+__global__ void unpack_v_kernel(const double* __restrict__ A, long long lda, int j0, int ib,
+                                int mrows, double* __restrict__ Vb) {
+  const long long total = (long long)mrows * ib;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % mrows), c = (int)(idx / mrows);
+    double v;
+    if (r < c)
+      v = 0.0;
+    else if (r == c)
+      v = 1.0;
+    else
+      v = A[(j0 + 1 + r) + (long long)(j0 + c) * lda];
+    Vb[r + (long long)c * mrows] = v;
+  }
+}
+
+// T (ib x ib upper triangular) from S = V'V and tau:  T[i,i] = tau_i,
+// T[0:i, i] = -tau_i * T[0:i,0:i] * S[0:i, i]
+__global__ void larft_kernel(const double* __restrict__ S, const double* __restrict__ tau, int ib,
+                             double* __restrict__ T) {
+  extern __shared__ double ts[];  // ib x ib
+  const int r = threadIdx.x;
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) ts[idx] = 0.0;
+  __syncthreads();
+  for (int i = 0; i < ib; ++i) {
+    const double ti = tau[i];
+    double acc = 0.0;
+    if (r < i) {
+      for (int q = r; q < i; ++q) acc = fma(ts[r + q * ib], S[q + (long long)i * ib], acc);
+    }
+    __syncthreads();
+    if (r < i) ts[r + i * ib] = -ti * acc;
+    if (r == i) ts[i + i * ib] = ti;
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[idx];
+}
+
+int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double* tau, double* Z,
+                long long ldz, int k) {
+  if (n <= 1 || k <= 0) return BK_OK;
+  const int IB = 64;
+  const int nref = n - 1;  // reflectors live in columns 0 .. n-2
+  DevBuf<double> Vb, S, T, W1, W2;
+  BK_TRY(Vb.alloc((size_t)n * IB));
+  BK_TRY(S.alloc((size_t)IB * IB));
+  BK_TRY(T.alloc((size_t)IB * IB));
+  BK_TRY(W1.alloc((size_t)IB * k));
+  BK_TRY(W2.alloc((size_t)IB * k));
+  const int nblocks = (int)ceil_div(nref, IB);
+  for (int b = nblocks - 1; b >= 0; --b) {
+    const int j0 = b * IB;
+    const int ib = std::min(IB, nref - j0);
+    const int mrows = n - j0 - 1;
+    const long long tot = (long long)mrows * ib;
+    unpack_v_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 256), 8LL * ctx->sm_count), 256, 0,
+                      ctx->stream>>>(A, lda, j0, ib, mrows, Vb.p);
+    BK_LAUNCHED(ctx);
+    BK_TRY(gemm(ctx, true, false, ib, ib, mrows, 1.0, Vb.p, mrows, Vb.p, mrows, 0.0, S.p, ib));
+    larft_kernel<<<1, 64, sizeof(double) * ib * ib, ctx->stream>>>(S.p, tau + j0, ib, T.p);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(cudaGetLastError());
+    double* Zb = Z + (j0 + 1);
+    BK_TRY(gemm(ctx, true, false, ib, k, mrows, 1.0, Vb.p, mrows, Zb, ldz, 0.0, W1.p, ib));
+    BK_TRY(gemm(ctx, false, false, ib, k, ib, 1.0, T.p, ib, W1.p, ib, 0.0, W2.p, ib));
+    BK_TRY(gemm(ctx, false, false, mrows, k, ib, -1.0, Vb.p, mrows, W2.p, ib, 1.0, Zb, ldz));
+  }
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work, long long ldw,
+               double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z,
+               long long ldz, EigenTimes* times) {
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  DevBuf<double> d, e, tau;
+  BK_TRY(d.alloc(n));
+  BK_TRY(e.alloc(n));
+  BK_TRY(tau.alloc(n));
+  BK_CUDA(cudaMemsetAsync(e.p, 0, sizeof(double) * n, ctx->stream));
+  BK_CUDA(cudaMemsetAsync(tau.p, 0, sizeof(double) * n, ctx->stream));
+  tm.start();
+  BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, work, ldw));
+  BK_TRY(sytrd_lower(ctx, work, ldw, n, d.p, e.p, tau.p, 64));
+  const double t_tri = tm.stop();
+  std::vector<double> dh(n), eh(n), ev(n);
+  BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(dh[i]) || !std::isfinite(eh[i])) {
+      set_error("eigen: tridiagonalisation produced a non-finite entry (NaN/Inf in the input?)");
+      return BK_ERR_NUMERIC;
+    }
+  tm.start();
+  int nw = 0;
+  StedcStats st;
+  BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
+  const double t_dc = tm.stop();
+  tm.start();
+  if (Z && nw > 0) BK_TRY(ormtr_lower(ctx, work, ldw, n, tau.p, Z, ldz, nw));
+  const double t_bt = tm.stop();
+  for (int i = 0; i < n; ++i) evals_host[i] = ev[n - 1 - i];
+  if (n_want) *n_want = nw;
+  if (times) {
+    times->tridiag = t_tri;
+    times->dc = t_dc;
+    times->backtransform = t_bt;
+    times->dc_stats = st;
+  }
+  return BK_OK;
+}
+
+}  // namespace bk
