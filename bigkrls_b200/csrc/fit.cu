@@ -18,6 +18,7 @@
 // in the Python host).
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <map>
 #include <cstring>
 #include "common.cuh"
@@ -119,15 +120,9 @@ double gs_step(GState& s, bool s1_less) {
 }
 
 struct LooEvaluator {
-  bk_ctx* ctx;
-  const bk_comm* comm;
-  const double* Q;  // row panel base (already offset to the first owned row)
-  long long ldq;
-  int n_rows, k;
-  const double* ev;  // device, first k eigenvalues
-  const double* z;   // device, Q'y
-  double* Le_dev;    // device, 16 doubles
-  int batch;
+  // evaluates Le for a batch of candidate lambdas (<= 16) into out[]
+  std::function<int(const std::vector<double>&, double*)> eval_batch;
+  int batch = 7;
   std::map<uint64_t, double> cache;
   int passes = 0;
 
@@ -140,10 +135,7 @@ struct LooEvaluator {
 
   int run(const std::vector<double>& lams) {
     double host[16];
-    BK_TRY(loo_batch(ctx, Q, ldq, n_rows, k, ev, z, lams.data(), (int)lams.size(), Le_dev, nullptr));
-    if (comm && comm->world > 1) COMM_CALL(comm->allreduce_sum(comm->user, Le_dev, 16), "allreduce(Le)");
-    BK_CUDA(cudaMemcpyAsync(host, Le_dev, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_TRY(eval_batch(lams, host));
     for (size_t i = 0; i < lams.size(); ++i) cache[key(lams[i])] = host[i];
     ++passes;
     return BK_OK;
@@ -151,6 +143,8 @@ struct LooEvaluator {
 
   // Le(lam); on a miss evaluates lam together with the speculative continuation of the search
   // tree rooted at `st` (breadth first, so the shallow levels are kept when the batch is full).
+  // Candidate points are produced by the same floating-point expressions the sequential search
+  // would use, so a later lookup hits the cache bit for bit.
   int get(double lam, const GState& st, const std::vector<double>& also, double* out) {
     if (!has(lam)) {
       std::vector<double> lams;
@@ -318,15 +312,15 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     BK_TRY(lambda_bounds(f->evals, n, &L, &U));
     const double tol = (o.tol > 0.0) ? o.tol : 1e-3 * n;  // R:10-12 (bigKRLS() never forwards tol)
     LooEvaluator le;
-    le.ctx = ctx;
-    le.comm = comm;
-    le.Q = f->Q.p + f->c0;
-    le.ldq = ld;
-    le.n_rows = nloc;
-    le.k = k;
-    le.ev = f->ev.p;
-    le.z = z.p;
-    le.Le_dev = Le_dev.p;
+    const double* Qpanel = f->Q.p + f->c0;
+    le.eval_batch = [&](const std::vector<double>& lams, double* out) -> int {
+      BK_TRY(loo_batch(ctx, Qpanel, ld, nloc, k, f->ev.p, z.p, lams.data(), (int)lams.size(),
+                       Le_dev.p, nullptr));
+      if (multi) COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
+      BK_CUDA(cudaMemcpyAsync(out, Le_dev.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+      return BK_OK;
+    };
     le.batch = std::max(1, std::min(15, o.loo_batch > 0 ? o.loo_batch : 7));
     BK_TRY(lambda_search(le, L, U, tol, &lam, &f->n_probes));
     f->n_passes = le.passes;
@@ -698,6 +692,60 @@ int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+
+// ---- host-logic hooks (no GPU needed): used by the CPU test-suite ---------------------------------
+int bk_host_lambda_search(const double* evals, int64_t neig, int64_t n, double L, double U, double tol,
+                          int batch, bk_le_callback cb, void* user, double* lambda, double* L_out,
+                          double* U_out, int* probes, int* passes) {
+  BK_REQUIRE(evals && cb && lambda && neig > 0 && n > 0, "bk_host_lambda_search: bad arguments");
+  std::vector<double> ev(evals, evals + neig);
+  BK_TRY(lambda_bounds(ev, (int)n, &L, &U));
+  if (L_out) *L_out = L;
+  if (U_out) *U_out = U;
+  LooEvaluator le;
+  le.batch = std::max(1, std::min(15, batch > 0 ? batch : 7));
+  le.eval_batch = [&](const std::vector<double>& lams, double* out) -> int {
+    if (cb(user, lams.data(), (int)lams.size(), out) != 0) {
+      set_error("bk_host_lambda_search: callback failed");
+      return BK_ERR_ARG;
+    }
+    return BK_OK;
+  };
+  int np = 0;
+  BK_TRY(lambda_search(le, L, U, tol > 0.0 ? tol : 1e-3 * (double)n, lambda, &np));
+  if (probes) *probes = np;
+  if (passes) *passes = le.passes;
+  return BK_OK;
+}
+
+int bk_host_deflate_test(const double* d, const double* z, int n, int n1, double beta, int* K,
+                         double* dlam, double* w, int32_t* nd_cols, int32_t* nd_type,
+                         int32_t* defl_cols, double* defl_vals, int* nrot, int32_t* rot_idx,
+                         double* rot_cs) {
+  BK_REQUIRE(d && z && K && n > 0 && n1 > 0 && n1 < n, "bk_host_deflate_test: bad arguments");
+  MergePlan plan;
+  host_deflate(d, z, n, n1, beta, &plan);
+  *K = plan.K;
+  for (int i = 0; i < plan.K; ++i) {
+    dlam[i] = plan.dlam[i];
+    w[i] = plan.w[i];
+    nd_cols[i] = plan.nd_cols[i];
+    nd_type[i] = plan.nd_type[i];
+  }
+  for (int i = 0; i < n - plan.K; ++i) {
+    defl_cols[i] = plan.defl_cols[i];
+    defl_vals[i] = plan.defl_vals[i];
+  }
+  *nrot = (int)plan.rots.size();
+  for (size_t i = 0; i < plan.rots.size(); ++i) {
+    rot_idx[2 * i] = plan.rots[i].pj;
+    rot_idx[2 * i + 1] = plan.rots[i].nj;
+    rot_cs[2 * i] = plan.rots[i].c;
+    rot_cs[2 * i + 1] = plan.rots[i].s;
+  }
   return BK_OK;
 }
 

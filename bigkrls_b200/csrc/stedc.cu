@@ -33,8 +33,8 @@ static constexpr int LEAF = 32;
 void host_deflate(const double* d_in, const double* z_in, int n, int n1, double beta,
                   MergePlan* plan) {
   std::vector<double> d(d_in, d_in + n), z(n);
-  const double inv_sqrt2 = 1.0 / std::sqrt(2.0);
-  for (int i = 0; i < n; ++i) z[i] = z_in[i] * inv_sqrt2;
+  const double sqrt2 = std::sqrt(2.0);
+  for (int i = 0; i < n; ++i) z[i] = z_in[i] / sqrt2;
   const double rho = std::fabs(2.0 * beta);
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);

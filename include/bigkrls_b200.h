@@ -183,7 +183,7 @@ BK_API int bk_fit_get_info(const bk_fit* f, bk_fit_info* info);
  * only that block (n x ncols, contiguous) - the caller places it (symmetric matrices:
  * column block == transposed row panel). */
 BK_API int bk_fit_col_range(const bk_fit* f, int64_t* c0, int64_t* c1);
-int bk_fit_get_K(const bk_fit* f, double* host);               /* kernel, n x (c1-c0) */
+BK_API int bk_fit_get_K(const bk_fit* f, double* host);               /* kernel, n x (c1-c0) */
 BK_API int bk_fit_get_eigenvalues(const bk_fit* f, double* host);     /* neig, descending */
 BK_API int bk_fit_get_eigenvectors(const bk_fit* f, double* host);    /* n x lastkeeper */
 BK_API int bk_fit_get_coeffs(const bk_fit* f, double* host);          /* n */
@@ -208,6 +208,20 @@ BK_API int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double*
  * generated data: C(m x n) = op(A) op(B). */
 BK_API int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower,
                    int iters, double* seconds);
+
+
+/* ---- host-logic hooks (pure CPU, no device needed) ------------------------------------------
+ * The golden-section search with speculative batching (fit.cu) and the divide-and-conquer
+ * deflation bookkeeping (stedc.cu) are host code; these two entry points expose them so the
+ * CPU test-suite can check them against the oracle / the numpy prototype without a GPU. */
+typedef int (*bk_le_callback)(void* user, const double* lambdas, int nlam, double* Le_out);
+BK_API int bk_host_lambda_search(const double* evals, int64_t neig, int64_t n, double L, double U, double tol,
+                          int batch, bk_le_callback cb, void* user, double* lambda, double* L_out,
+                          double* U_out, int* probes, int* passes);
+BK_API int bk_host_deflate_test(const double* d, const double* z, int n, int n1, double beta, int* K,
+                         double* dlam, double* w, int32_t* nd_cols, int32_t* nd_type,
+                         int32_t* defl_cols, double* defl_vals, int* nrot, int32_t* rot_idx,
+                         double* rot_cs);
 
 #ifdef __cplusplus
 }

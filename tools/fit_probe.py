@@ -1,0 +1,26 @@
+"""Time one fused fit at (N, P) on the GPU and print the per-stage break-down."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import numpy as np  # noqa: E402
+
+from bigkrls_b200 import bigKRLS  # noqa: E402
+import krls_oracle as o  # noqa: E402
+
+N, P = int(sys.argv[1]), int(sys.argv[2])
+kw = {}
+if len(sys.argv) > 3:
+    kw["eigtrunc"] = float(sys.argv[3])
+X, y = o.synthetic(N, P, 1000 + P)
+for rep in range(2):
+    t0 = time.time()
+    fit = bigKRLS(y, X, return_squares=False, **kw)
+    t1 = time.time()
+    info = fit["_info"]
+    fit.release_device()
+    print(json.dumps({"N": N, "P": P, "wall": t1 - t0, **{k: (round(v, 6) if isinstance(v, float) else v)
+                                                       for k, v in info.items()}}))
