@@ -321,8 +321,8 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
   const int tiles = (int)(ceil_div(m, bm) * ceil_div(n, bn));
   // deterministic split-K when the tile grid cannot fill the machine and k is long
   int splits = 1;
-  if (!lower && tiles < ctx->sm_count && k >= 1024) {
-    splits = (int)std::min<int64_t>(ceil_div(2 * ctx->sm_count, tiles), k / 256);
+  if (!lower && tiles < 2 * ctx->sm_count && k >= 1024) {
+    splits = (int)std::min<int64_t>(ceil_div(4 * ctx->sm_count, tiles), k / 256);
     splits = std::max(1, std::min(splits, 64));
   }
   double* ws = nullptr;
