@@ -55,7 +55,11 @@ class FitInfo(C.Structure):
                 ("t_kernel", C.c_double), ("t_eigen", C.c_double), ("t_lambda", C.c_double),
                 ("t_coef", C.c_double), ("t_vcov", C.c_double), ("t_deriv", C.c_double),
                 ("t_total", C.c_double),
-                ("t_tridiag", C.c_double), ("t_dc", C.c_double), ("t_backtransform", C.c_double)]
+                ("t_tridiag", C.c_double), ("t_dc", C.c_double), ("t_backtransform", C.c_double),
+                ("sytrd_launches", C.c_double), ("sytrd_kernel_seconds", C.c_double),
+                ("sytrd_bytes", C.c_double),
+                ("dc_levels", C.c_double), ("dc_merge_flops", C.c_double), ("dc_top_n", C.c_double),
+                ("dc_top_k", C.c_double), ("gpu_launches", C.c_double)]
 
     def as_dict(self):
         d = {}
@@ -71,6 +75,7 @@ _SIGNATURES = {
     "bk_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "bk_destroy": (None, [C.c_void_p]),
     "bk_device_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), c_int64_p, c_int64_p]),
+    "bk_launch_count": (C.c_int64, [C.c_void_p]),
     "bk_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "bk_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bk_gauss_kernel": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, C.c_double, c_double_p]),
@@ -113,6 +118,10 @@ _SIGNATURES = {
     "bk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_double_p]),
     "bk_dgemm_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                  C.c_int, c_double_p]),
+    "bk_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p,
+                                C.c_int64, c_double_p, C.c_int64, C.c_double, c_double_p, C.c_int64, C.c_int, C.c_int]),
+    "bk_debug_sytrd": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "bk_debug_stedc": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
     "bk_host_lambda_search": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                         C.c_int, C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -194,4 +194,50 @@ int bk_neffective(bk_ctx* ctx, const double* X, int64_t n, int64_t p, double* ou
   return neffective_acf(ctx, dX.p, n, (int)n, (int)p, out);
 }
 
+
+int bk_debug_gemm(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower,
+                  int repeats) {
+  BK_TRY(enter(ctx, "bk_debug_gemm"));
+  BK_REQUIRE(A && B && C && m > 0 && n > 0 && k > 0, "bk_debug_gemm: bad arguments");
+  const int64_t a_cols = ta ? m : k, b_cols = tb ? k : n;
+  DevBuf<double> dA, dB, dC, dC0;
+  BK_TRY(h2d(ctx, dA, A, (size_t)lda * a_cols));
+  BK_TRY(h2d(ctx, dB, B, (size_t)ldb * b_cols));
+  BK_TRY(h2d(ctx, dC0, C, (size_t)ldc * n));
+  BK_TRY(dC.alloc((size_t)ldc * n));
+  for (int r = 0; r < std::max(1, repeats); ++r) {
+    BK_CUDA(cudaMemcpyAsync(dC.p, dC0.p, sizeof(double) * (size_t)ldc * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    BK_TRY(gemm(ctx, ta != 0, tb != 0, (int)m, (int)n, (int)k, alpha, dA.p, lda, dB.p, ldb, beta, dC.p, ldc,
+                lower != 0));
+  }
+  return d2h(ctx, C, dC.p, (size_t)ldc * n);
+}
+
+int bk_debug_sytrd(bk_ctx* ctx, const double* A, int64_t n, double* d, double* e) {
+  BK_TRY(enter(ctx, "bk_debug_sytrd"));
+  BK_REQUIRE(A && d && e && n > 0 && fits_int(n), "bk_debug_sytrd: bad arguments");
+  DevBuf<double> dA, dd, de, dt;
+  BK_TRY(h2d(ctx, dA, A, (size_t)n * n));
+  BK_TRY(dd.alloc(n));
+  BK_TRY(de.alloc(n));
+  BK_TRY(dt.alloc(n));
+  BK_CUDA(cudaMemsetAsync(de.p, 0, sizeof(double) * n, ctx->stream));
+  BK_TRY(sytrd_lower(ctx, dA.p, n, (int)n, dd.p, de.p, dt.p, 64, nullptr));
+  BK_TRY(d2h(ctx, d, dd.p, n));
+  if (n > 1) BK_TRY(d2h(ctx, e, de.p, n - 1));
+  return BK_OK;
+}
+
+int bk_debug_stedc(bk_ctx* ctx, const double* d, const double* e, int64_t n, double* evals, double* Z) {
+  BK_TRY(enter(ctx, "bk_debug_stedc"));
+  BK_REQUIRE(d && e && evals && n > 0 && fits_int(n), "bk_debug_stedc: bad arguments");
+  DevBuf<double> dZ;
+  if (Z) BK_TRY(dZ.alloc((size_t)n * n));
+  int nw = 0;
+  BK_TRY(stedc(ctx, (int)n, d, e, evals, Z ? (int)n : 0, -INFINITY, &nw, Z ? dZ.p : nullptr, n, nullptr));
+  if (Z) BK_TRY(d2h(ctx, Z, dZ.p, (size_t)n * n));
+  return BK_OK;
+}
+
 }  // extern "C"

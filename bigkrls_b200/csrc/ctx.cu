@@ -80,6 +80,8 @@ int bk_device_info(bk_ctx* ctx, char* name, int name_len, int* sm_count, int64_t
   return BK_OK;
 }
 
+int64_t bk_launch_count(bk_ctx* ctx) { return ctx ? (int64_t)ctx->n_launches : 0; }
+
 int bk_host_alloc(bk_ctx* ctx, int64_t bytes, void** out) {
   BK_REQUIRE(ctx && out && bytes > 0, "bk_host_alloc: bad arguments");
   BK_CUDA(cudaSetDevice(ctx->device));

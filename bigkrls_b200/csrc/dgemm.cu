@@ -19,6 +19,7 @@
 // Variants: transposed operands, batched (array of problem descriptors, blockIdx.z),
 // lower-triangle-only tile skipping (SYRK/SYR2K-like updates), deterministic split-K for
 // short-and-wide reductions (partials to a workspace, fixed-order reduce).
+#include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
 
@@ -270,6 +271,8 @@ static int dispatch(bk_ctx* ctx, bool ta, bool tb, bool vec, const GemmProb& sin
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 bool gemm_operands_vec_ok(const void* A, long long lda, const void* B, long long ldb) {
+  static const bool novec = getenv("BK_GEMM_NOVEC") != nullptr;
+  if (novec) return false;
   return aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
 }
 

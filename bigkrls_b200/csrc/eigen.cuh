@@ -6,8 +6,13 @@ namespace bk {
 
 // A (n x n, lower triangle referenced and overwritten) -> d[n], e[n-1], tau[n-1] (device);
 // reflectors stored LAPACK-style below the first sub-diagonal of A.
+struct SytrdStats {
+  int launches = 0;
+  double kernel_seconds = 0;     // sum of the panel-kernel durations (CUDA events)
+  double algorithmic_bytes = 0;  // sum_j 4 (n-1-j)^2: the lower triangle read once per column
+};
 int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double* e, double* tau,
-                int nb);
+                int nb, SytrdStats* stats);
 
 struct StedcStats {
   int levels = 0;
@@ -31,6 +36,7 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
 struct EigenTimes {
   double tridiag = 0, dc = 0, backtransform = 0;
   StedcStats dc_stats;
+  SytrdStats sytrd;
 };
 
 // Full path: K (n x n symmetric, device, preserved) -> evals_host[n] DESCENDING and the

@@ -220,6 +220,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   BK_TRY(total.init(ctx->stream));
   total.start();
   memset(&f->info, 0, sizeof(f->info));
+  const uint64_t launches0 = ctx->n_launches;
 
   // ---- 1/5 kernel -------------------------------------------------------------------------
   tm.start();
@@ -258,6 +259,13 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
       f->info.t_tridiag = et.tridiag;
       f->info.t_dc = et.dc;
       f->info.t_backtransform = et.backtransform;
+      f->info.sytrd_launches = et.sytrd.launches;
+      f->info.sytrd_kernel_seconds = et.sytrd.kernel_seconds;
+      f->info.sytrd_bytes = et.sytrd.algorithmic_bytes;
+      f->info.dc_levels = et.dc_stats.levels;
+      f->info.dc_merge_flops = (double)et.dc_stats.merge_flops;
+      f->info.dc_top_n = et.dc_stats.top_n;
+      f->info.dc_top_k = et.dc_stats.top_k;
     }
     BK_TRY(f->ev.alloc(f->neig + 1));
     if (multi) {
@@ -477,6 +485,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   f->info.neffective = f->neffective;
   f->info.n_probes = f->n_probes;
   f->info.n_passes = f->n_passes;
+  f->info.gpu_launches = (double)(ctx->n_launches - launches0);
   return BK_OK;
 }
 

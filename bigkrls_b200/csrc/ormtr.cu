@@ -100,7 +100,8 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work,
   BK_CUDA(cudaMemsetAsync(tau.p, 0, sizeof(double) * n, ctx->stream));
   tm.start();
   BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, work, ldw));
-  BK_TRY(sytrd_lower(ctx, work, ldw, n, d.p, e.p, tau.p, 64));
+  SytrdStats sst;
+  BK_TRY(sytrd_lower(ctx, work, ldw, n, d.p, e.p, tau.p, 64, &sst));
   const double t_tri = tm.stop();
   std::vector<double> dh(n), eh(n), ev(n);
   BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -126,6 +127,7 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work,
     times->dc = t_dc;
     times->backtransform = t_bt;
     times->dc_stats = st;
+    times->sytrd = sst;
   }
   return BK_OK;
 }

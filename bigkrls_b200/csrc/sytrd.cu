@@ -17,11 +17,13 @@
 //
 // Layout: A column-major n x n; panel workspace P = [V | W | V] (n x 3nb) so that the rank-2nb
 // update is ONE GEMM  A22 -= P[:,0:2nb] * P[:,nb:3nb]'.  Reflector j is stored LAPACK-style in
-// A[j+2:, j] (v[j+1] = 1 implicit), e[j] = beta, d[j] = A[j,j].
+// A[j+2:, j] (v[j+1] = 1 implicit; A[j+1, j] is left holding alpha), e[j] = beta, d[j] = A[j,j].
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
 #include "eigen.cuh"
+#include "kernels.cuh"
 
 namespace bk {
 
@@ -43,6 +45,8 @@ struct SytrdArgs {
 };
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+// data written by other CTAs earlier in this kernel is always read through L2
+#define LDX(p) __ldcg(p)
 
 __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
   __shared__ double red[32];
@@ -76,13 +80,13 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
     for (int r = j + gid; r < n; r += gthreads) {
       if (c > 0) {
         double* wp = W + (size_t)(c - 1) * n;
-        wp[r] = wp[r] + alpha_prev * V[(size_t)(c - 1) * n + r];
+        wp[r] = LDX(wp + r) + alpha_prev * LDX(V + (size_t)(c - 1) * n + r);
       }
       double v = A[r + (long long)j * lda];
       for (int q = 0; q < c; ++q) {
         const double wjq = (q == c - 1) ? wjc : ldcg(W + (size_t)q * n + j);
         const double vjq = ldcg(V + (size_t)q * n + j);
-        v -= V[(size_t)q * n + r] * wjq + W[(size_t)q * n + r] * vjq;
+        v -= LDX(V + (size_t)q * n + r) * wjq + LDX(W + (size_t)q * n + r) * vjq;
       }
       A[r + (long long)j * lda] = v;
       if (r == j) a.d[j] = v;
@@ -115,8 +119,9 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
     for (int r = j + 1 + gid; r < n; r += gthreads) {
       double v;
       if (r == j + 1) {
+        // A[j+1, j] keeps alpha: every CTA reads it at the top of this phase, so it must not be
+        // overwritten here (beta lives in e[j]; the back-transform uses an explicit 1).
         v = 1.0;
-        A[r + (long long)j * lda] = beta;
       } else {
         v = ldcg(A + r + (long long)j * lda) * scale;
         A[r + (long long)j * lda] = v;
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
     for (int q = blockIdx.x; q < 2 * c; q += G) {
       const double* col = (q < c) ? (W + (size_t)q * n) : (V + (size_t)(q - c) * n);
       double s = 0.0;
-      for (int r = j + 1 + threadIdx.x; r < n; r += blockDim.x) s += col[r] * ldcg(vcol + r);
+      for (int r = j + 1 + threadIdx.x; r < n; r += blockDim.x) s += LDX(col + r) * ldcg(vcol + r);
       s = block_sum(s, red);
       if (threadIdx.x == 0) a.dots[(q < c) ? q : (nb + q - c)] = s;
     }
@@ -217,11 +222,11 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
         for (int bcx = t0; bcx <= br; ++bcx) y += ldcg(a.ypart + (size_t)bcx * n + r);
         for (int sbx = (br - t0) / S; sbx < NSEG; ++sbx) y += ldcg(a.ytpart + (size_t)sbx * n + r);
         for (int q = 0; q < c; ++q)
-          y -= V[(size_t)q * n + r] * ldcg(a.dots + q) + W[(size_t)q * n + r] * ldcg(a.dots + nb + q);
+          y -= LDX(V + (size_t)q * n + r) * ldcg(a.dots + q) + LDX(W + (size_t)q * n + r) * ldcg(a.dots + nb + q);
         const double w = tau * y;
         W[(size_t)c * n + r] = w;
         if (r == j + 1) a.dots[2 * nb] = w;
-        wv += w * vcol[r];
+        wv += w * ldcg(vcol + r);
       }
       wv = block_sum(wv, red);
       if (threadIdx.x == 0) a.part[G + blockIdx.x] = wv;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
 }
 
 int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double* e, double* tau,
-                int nb) {
+                int nb, SytrdStats* stats) {
   if (n <= 0) return BK_OK;
   if (n == 1) {
     BK_CUDA(cudaMemcpyAsync(d, A, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -252,6 +257,7 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
   BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel, 256, 0));
   BK_REQUIRE(occ >= 1, "sytrd: kernel does not fit on an SM");
   occ = std::min(occ, 2);
+  if (const char* ev = getenv("BK_SYTRD_OCC")) occ = std::max(1, std::min(occ, atoi(ev)));
   const int G = ctx->sm_count * occ;
   const int T = (int)ceil_div(n, TS);
   const int TSEG = T;  // upper bound on the number of row segments (S >= 1)
@@ -263,7 +269,14 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
   BK_TRY(ytpart.alloc((size_t)TSEG * n));
   BK_TRY(ctx->barrier.ensure(4));
 
-  for (int j0 = 0; j0 < n; j0 += nb) {
+  // per-panel CUDA events on the launching stream: the roofline numbers of bench.py are the
+  // sum of these kernel durations against the algorithmic bytes 4 m_j^2 per column
+  const int npanels = (int)ceil_div(n, nb);
+  std::vector<cudaEvent_t> ev0(stats ? npanels : 0), ev1(stats ? npanels : 0);
+  for (auto& x : ev0) BK_CUDA(cudaEventCreate(&x));
+  for (auto& x : ev1) BK_CUDA(cudaEventCreate(&x));
+  int pi = 0;
+  for (int j0 = 0; j0 < n; j0 += nb, ++pi) {
     BK_CUDA(cudaMemsetAsync(P.p, 0, sizeof(double) * (size_t)3 * nb * n, ctx->stream));
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
     SytrdArgs args;
@@ -282,8 +295,10 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     args.ytpart = ytpart.p;
     args.barrier = ctx->barrier.p;
     void* kargs[] = {&args};
+    if (stats) BK_CUDA(cudaEventRecord(ev0[pi], ctx->stream));
     BK_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(G), dim3(256), kargs, 0,
                                         ctx->stream));
+    if (stats) BK_CUDA(cudaEventRecord(ev1[pi], ctx->stream));
     BK_LAUNCHED(ctx);
     const int jn = j0 + nb;
     if (jn < n) {
@@ -294,6 +309,22 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     }
   }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));  // workspaces are freed on return
+  if (stats) {
+    stats->launches = npanels;
+    stats->kernel_seconds = 0.0;
+    stats->algorithmic_bytes = 0.0;
+    for (int i = 0; i < npanels; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev0[i], ev1[i]);
+      stats->kernel_seconds += 1e-3 * ms;
+      cudaEventDestroy(ev0[i]);
+      cudaEventDestroy(ev1[i]);
+    }
+    for (int j = 0; j < n - 1; ++j) {
+      const double m = (double)(n - 1 - j);
+      stats->algorithmic_bytes += 4.0 * m * m;  // lower triangle (incl. diagonal ~ m^2/2 doubles)
+    }
+  }
   return BK_OK;
 }
 

@@ -60,6 +60,8 @@ BK_API void bk_destroy(bk_ctx* ctx);
 BK_API int bk_device_info(bk_ctx* ctx, char* name, int name_len, int* sm_count, int64_t* hbm_total,
                    int64_t* hbm_free);
 /* pinned host memory for the caller's staging buffers (D2H of the N x N outputs) */
+/* number of kernels this context has launched so far (bench.py's "gpu_launches") */
+BK_API int64_t bk_launch_count(bk_ctx* ctx);
 BK_API int bk_host_alloc(bk_ctx* ctx, int64_t bytes, void** out);
 BK_API int bk_host_free(bk_ctx* ctx, void* p);
 
@@ -166,6 +168,13 @@ typedef struct bk_fit_info {
   double t_kernel, t_eigen, t_lambda, t_coef, t_vcov, t_deriv, t_total;
   /* eigensolver break-down */
   double t_tridiag, t_dc, t_backtransform;
+  /* dominant kernel (tridiagonalisation panel kernel): launches, summed device time of those
+   * launches (CUDA events on the launching stream) and their algorithmic HBM bytes */
+  double sytrd_launches, sytrd_kernel_seconds, sytrd_bytes;
+  /* divide & conquer: tree levels, flops of the merge GEMMs, size / non-deflated count of the root merge */
+  double dc_levels, dc_merge_flops, dc_top_n, dc_top_k;
+  /* kernels launched by the library during this fit */
+  double gpu_launches;
 } bk_fit_info;
 
 /* Xs (n x p) and ys (n) are the STANDARDISED data (R/bigKRLS.R:251-254), host pointers.
@@ -209,6 +218,15 @@ BK_API int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double*
 BK_API int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower,
                    int iters, double* seconds);
 
+/* Stage-level hooks of the eigensolver (tests/test_gpu_eigen_stages.py): tridiagonalisation only
+ * (A n x n host -> d[n], e[n-1]) and divide & conquer only (d, e host -> evals ascending, Z n x n
+ * eigenvectors of the tridiagonal, column c <-> c-th LARGEST; Z may be NULL). */
+/* general library GEMM on host buffers, C (in/out) = alpha op(A) op(B) + beta C, optional lower-tile mode */
+BK_API int bk_debug_gemm(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower,
+                  int repeats);
+BK_API int bk_debug_sytrd(bk_ctx* ctx, const double* A, int64_t n, double* d, double* e);
+BK_API int bk_debug_stedc(bk_ctx* ctx, const double* d, const double* e, int64_t n, double* evals, double* Z);
 
 /* ---- host-logic hooks (pure CPU, no device needed) ------------------------------------------
  * The golden-section search with speculative batching (fit.cu) and the divide-and-conquer

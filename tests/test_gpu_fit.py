@@ -56,7 +56,7 @@ def test_mtcars_reference_known_answers():
     (1200, 6, 2, dict(eigtrunc=0.001)),
     (800, 4, 3, dict(eigtrunc=0, binary=True)),
     (900, 8, 4, dict(eigtrunc=0.01, which_derivatives=[1, 3, 5])),
-    (600, 3, 5, dict(lambda_=0.5)),
+    (600, 5, 5, dict(lambda_=0.5)),
     (3100, 5, 6, dict()),                       # n > 3000 -> default eigtrunc = 0.001
 ])
 def test_fit_parity_synthetic(n, p, seed, kw):
