@@ -83,7 +83,7 @@ def temp_kernel(A, B, sigma):
 # --------------------------------------------------------------------------------------
 # a3 eigen (src/eigen.cpp:18-29, R/bigKRLS_Rcpp_functions.R:173-199)
 # --------------------------------------------------------------------------------------
-def eigen(K, Neig=None, eigtrunc=0.0):
+def eigen(K, Neig=None, eigtrunc=0.0, force_lastkeeper=None):
     """arma::eig_sym (LAPACK dsyevd) then flip to descending (src/eigen.cpp:24,28-29).
 
     For Neig < N the reference calls arma::eigs_sym (largest magnitude, tol = eps): the
@@ -103,6 +103,12 @@ def eigen(K, Neig=None, eigtrunc=0.0):
         vals, vecs = vals[:Neig], vecs[:, :Neig]
     vecs = -1.0 * vecs
     lastkeeper = int(np.max(np.nonzero(vals >= eigtrunc * vals[0])[0])) + 1
+    if force_lastkeeper is not None:
+        # test aid: with eigtrunc = 0 and a numerically singular K the reference's rule
+        # `max(which(values >= 0))` is decided by the SIGN OF ROUNDING NOISE in eigenvalues of
+        # size ~1e-16*lambda_1 (two LAPACK builds disagree); parity is then checked at equal
+        # lastkeeper.
+        lastkeeper = int(force_lastkeeper)
     return {"values": vals, "vectors": np.asfortranarray(vecs[:, :lastkeeper]),
             "lastkeeper": lastkeeper}
 
@@ -284,7 +290,8 @@ def neffective_acf(X):
 # bigKRLS() driver  (R/bigKRLS.R:97-516)
 # --------------------------------------------------------------------------------------
 def bigkrls(y, X, sigma=None, derivative=True, which_derivatives=None, vcov_est=True,
-            Neig=None, eigtrunc=None, lam=None, L=None, U=None, acf=False, literal=False):
+            Neig=None, eigtrunc=None, lam=None, L=None, U=None, acf=False, literal=False,
+            force_lastkeeper=None):
     """Returns a dict with the reference's output-list field names (R/bigKRLS.R:420-469).
 
     `which_derivatives` is 1-based like R.  Quirk B.1 (X.init.sd[i] index bug,
@@ -302,7 +309,7 @@ def bigkrls(y, X, sigma=None, derivative=True, which_derivatives=None, vcov_est=
     x_is_binary = binary_indicator(X0)                                   # :242
     Xs, ys, xm, xs, y_mean, y_sd = standardize(X0, y0)                   # :245-254
     K = gauss_kernel(Xs, sigma)                                          # :262
-    eo = eigen(K, Neig, eigtrunc)                                        # :266
+    eo = eigen(K, Neig, eigtrunc, force_lastkeeper)                      # :266
     w["K.eigenvalues"] = eo["values"]
     w["lastkeeper"] = eo["lastkeeper"]
     nprobe = 0
