@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: bigKRLS() fit wall-seconds at N=20k, P=10 (BASELINE.json configs[2]:
+eigtrunc=0.001, all derivatives), 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One step = one full fit (kernel -> eigen -> lambda -> coefficients + vcov -> marginal effects) of
+the same synthetic workload (SURVEY.md 8d generator, seed 1003).
+
+  value  seconds per fit with the standardised inputs already resident in HBM
+         (bk_fit_run_device), wall clock bracketed by barrier + synchronize, max over ranks
+  e2e    seconds per fit through the public API bigKRLS(y, X) with HOST buffers: standardise,
+         H2D of X/y, fit, D2H of every output field incl. the three N x N matrices (pinned
+         host buffers from the library's pool)
+  roofline  dominant kernel = the tridiagonalisation panel kernel (symmetric mat-vec): algorithmic
+         bytes (lower triangle once per column: sum_j 4 (N-1-j)^2) / summed CUDA-event duration of
+         its launches, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the compiled literal restatement of the reference (oracle/krls_port.cpp, OpenBLAS,
+         all host threads) on a bounded sample, scaled cubically to the metric's size
+
+Nothing under oracle/ is on the measured CUDA path: it is executed only for `cpu_baseline`
+and `--impl reference`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_FULL, P_FULL, SEED, EIGTRUNC = 20000, 10, 1003, 0.001
+METRIC = "bigKRLS() fit wall-s at N=20k P=10"
+
+
+def synthetic(N, P, seed):
+    """SURVEY.md 8d generator (identical to oracle/krls_oracle.synthetic; duplicated here so the
+    CUDA arm never imports oracle/)."""
+    rng = np.random.default_rng(seed)
+    X0 = rng.standard_normal((N, P))
+    eps = rng.standard_normal(N)
+    y0 = np.sin(X0[:, 0]) + X0[:, 1] * X0[:, 2] + 0.5 * eps
+    return np.asfortranarray(X0), y0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_sample(n_sample, threads):
+    """Times the compiled literal restatement of the reference on n_sample rows of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import krls_oracle as o   # CPU baseline leg only
+    import port
+    X, y = synthetic(N_FULL, P_FULL, SEED)
+    X, y = X[:n_sample], y[:n_sample]
+    Xs, ys, *_ = o.standardize(X, y)
+    t0 = time.perf_counter()
+    r = port.fit(Xs, ys, eigtrunc=EIGTRUNC, threads=threads)
+    return time.perf_counter() - t0, r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ns = args.sample_n
+    scale = (N_FULL / ns) ** 3
+    for _ in range(args.warmup):
+        cpu_port_sample(min(ns, 1000), threads)
+    ts = []
+    stages = None
+    for _ in range(args.steps):
+        t, r = cpu_port_sample(ns, threads)
+        ts.append(t)
+        stages = r["times"]
+    sec = float(np.mean(ts)) * scale
+    sample = (f"first {ns} rows of the N={N_FULL} P={P_FULL} workload, all stages with the reference's O(N^3)-per-"
+              f"column structure; measured {np.mean(ts):.2f} s/fit, scaled x(N/{ns})^3 = x{scale:.1f} to N={N_FULL}")
+    line = {"impl": "reference", "metric": METRIC, "value": sec, "unit": "s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ts)) * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"bigKRLS N={N_FULL} P={P_FULL} eigtrunc={EIGTRUNC} all derivatives"},
+            "cpu_baseline": {"value": sec, "unit": "s", "cores": threads, "kind": "port", "sample": sample,
+                             "stage_seconds_on_sample": {k: float(v) for k, v in stages.items()},
+                             "blas": "OpenBLAS (scipy wheel) dsyevd/dgemm/dgemv"},
+            "e2e": {"value": sec, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL)
+    ap.add_argument("--p", type=int, default=P_FULL)
+    ap.add_argument("--sample-n", type=int, default=3000, help="rows of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import ctypes as C
+    from bigkrls_b200 import _lib, bigKRLS
+    from bigkrls_b200._lib import FitInfo, FitOpts, check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        from bigkrls_b200.dist import TorchComm
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = TorchComm(device=f"cuda:{local}")
+    N, P = args.n, args.p
+    lib = _lib.load()
+    ctx = _lib.default_context(local)
+    X, y = synthetic(N, P, SEED)
+    xsd, ysd = np.std(X, axis=0, ddof=1), float(np.std(y, ddof=1))
+    Xs = np.asfortranarray((X - X.mean(axis=0)) / xsd)
+    ys = (y - y.mean()) / ysd
+    dX = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()     # column-major N x P == row-major P x N
+    dy = torch.from_numpy(ys).cuda()
+    opts = FitOpts()
+    lib.bk_fit_default_opts(C.byref(opts), N, P)
+    opts.eigtrunc = EIGTRUNC
+    opts.y_sd = ysd
+    cptr = C.byref(comm.struct) if comm is not None else None
+
+    def sync():
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+            torch.cuda.synchronize()
+
+    def resident_step():
+        h = C.c_void_p()
+        check(lib.bk_fit_run_device(ctx.handle, C.c_void_p(dX.data_ptr()), C.c_void_p(dy.data_ptr()), N, P,
+                                    C.byref(opts), cptr, C.byref(h)))
+        info = FitInfo()
+        check(lib.bk_fit_get_info(h, C.byref(info)))
+        lib.bk_fit_free(h)
+        return info.as_dict()
+
+    def e2e_step():
+        fit = bigKRLS(y, X, eigtrunc=EIGTRUNC, comm=comm, pinned=True, ctx=ctx)
+        d2h = sum(fit[k].nbytes for k in ("K", "vcov.est.c", "vcov.est.fitted", "derivatives", "coeffs", "yfitted")
+                  if k in fit) + fit["K.eigenvalues"].nbytes
+        fit.release_device()
+        fit.release_pinned()
+        return d2h
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local)
+    sync()
+    launches0 = lib.bk_launch_count(ctx.handle)
+    sampler.start()
+    t0 = time.perf_counter()
+    infos = [resident_step() for _ in range(args.steps)]
+    sync()
+    t1 = time.perf_counter()
+    clocks = sampler.stop()
+    launches = lib.bk_launch_count(ctx.handle) - launches0
+    sec = (t1 - t0) / args.steps
+
+    e2e_step()                                   # warm the pinned pool
+    sync()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = e2e_step()
+    sync()
+    e2e_sec = (time.perf_counter() - t0) / args.steps
+
+    if comm is not None:
+        t = torch.tensor([sec, e2e_sec], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        sec, e2e_sec = t.tolist()
+    if rank != 0:
+        return
+    info = infos[-1]
+    peak, peak_src = measured_peaks()
+    ach = info["sytrd_bytes"] / info["sytrd_kernel_seconds"] * 1e-9 if info["sytrd_kernel_seconds"] > 0 else 0.0
+    stage = {k: float(np.mean([i[k] for i in infos])) for k in
+             ("t_kernel", "t_eigen", "t_tridiag", "t_dc", "t_backtransform", "t_lambda", "t_coef", "t_vcov",
+              "t_deriv", "t_total")}
+    line = {"metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"bigKRLS N={N} P={P} eigtrunc={EIGTRUNC} all derivatives (BASELINE.json configs[2])",
+                       "seed": SEED, "l2": "inputs larger than L2 (K is %.1f GB)" % (8.0 * N * N * 1e-9),
+                       "parallelism": f"column-block x{world}, eigensolver on rank 0"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "sytrd_panel_kernel (symmetric mat-vec of the tridiagonalisation)", "bound": "hbm",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "launches_per_step": int(info["sytrd_launches"]),
+                         "algorithmic_bytes_per_launch": info["sytrd_bytes"] / max(1.0, info["sytrd_launches"]),
+                         "avg_launch_seconds": info["sytrd_kernel_seconds"] / max(1.0, info["sytrd_launches"]),
+                         "traffic": None},
+            "stage_seconds": stage,
+            "fit": {"lambda": info["lambda"], "lastkeeper": int(info["lastkeeper"]), "n_probes": info["n_probes"],
+                    "n_passes": info["n_passes"], "dc_top_k": int(info["dc_top_k"])}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ns = args.sample_n
+        t, r = cpu_port_sample(ns, threads)
+        scale = (N / ns) ** 3
+        line["cpu_baseline"] = {"value": t * scale, "unit": "s", "cores": threads, "kind": "port",
+                                "sample": f"first {ns} rows of the workload, literal reference structure "
+                                          f"(oracle/krls_port.cpp, OpenBLAS); measured {t:.2f} s, scaled x{scale:.1f} "
+                                          f"((N/{ns})^3) to N={N}",
+                                "stage_seconds_on_sample": {k: float(v) for k, v in r["times"].items()}}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if comm is not None:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -199,23 +199,35 @@ class Context:
                 "hbm_free": free.value}
 
     def pinned_empty(self, shape, order="F"):
-        """float64 array in pinned host memory (freed when the array's base dies)."""
+        """float64 array in pinned (page-locked) host memory.  Buffers come from a per-context
+        pool: recycle_pinned(arr) returns one for reuse (cudaHostAlloc of GBs is slow)."""
         n = int(np.prod(shape))
-        p = C.c_void_p()
-        check(self._lib.bk_host_alloc(self.handle, max(8, 8 * n), C.byref(p)))
-        buf = (C.c_double * n).from_address(p.value)
+        nbytes = max(8, 8 * n)
+        pool = self.__dict__.setdefault("_pool", {})
+        if pool.get(nbytes):
+            addr = pool[nbytes].pop()
+        else:
+            p = C.c_void_p()
+            check(self._lib.bk_host_alloc(self.handle, nbytes, C.byref(p)))
+            addr = p.value
+        buf = (C.c_double * n).from_address(addr)
         arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
-        _PINNED[p.value] = (self, buf)
+        self.__dict__.setdefault("_live", {})[addr] = nbytes
         return arr
 
-    def free_pinned(self, arr):
+    def recycle_pinned(self, arr):
+        """Give a pinned_empty() array back to the pool (the caller must drop its references)."""
         addr = arr.ctypes.data
-        if addr in _PINNED:
-            del _PINNED[addr]
-            check(self._lib.bk_host_free(self.handle, C.c_void_p(addr)))
+        live = self.__dict__.get("_live", {})
+        if addr in live:
+            self.__dict__.setdefault("_pool", {}).setdefault(live.pop(addr), []).append(addr)
+
+    def drain_pinned(self):
+        for lst in self.__dict__.get("_pool", {}).values():
+            while lst:
+                self._lib.bk_host_free(self.handle, C.c_void_p(lst.pop()))
 
 
-_PINNED = {}
 _default_ctx = {}
 
 

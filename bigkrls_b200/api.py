@@ -42,6 +42,13 @@ class BigKRLS(dict):
             _lib.load().bk_fit_free(self._fit)
             self._fit = None
 
+    def release_pinned(self):
+        """Return pinned output buffers (pinned=True fits) to the context's pool."""
+        for k in ("K", "vcov.est.c", "vcov.est.fitted"):
+            a = self.pop(k, None)
+            if a is not None and self._ctx is not None and self.get("_pinned"):
+                self._ctx.recycle_pinned(a)
+
     def __del__(self):
         try:
             self.release_device()
@@ -206,6 +213,7 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
             Vf = alloc((n, ncols))
             check(lib.bk_fit_get_vcov_fitted(h, dptr(Vf)))
             w["vcov.est.fitted"] = Vf
+    w["_pinned"] = bool(pinned)
     w["derivative.call"] = bool(derivative)                                     # :455
     if not keep_device:
         w.release_device()
