@@ -64,15 +64,14 @@ int bk_eigen(bk_ctx* ctx, const double* A, int64_t n, int64_t neig, double* vals
   BK_TRY(enter(ctx, "bk_eigen"));
   BK_REQUIRE(A && vals && n > 0 && fits_int(n), "bk_eigen: bad arguments");
   BK_REQUIRE(neig >= 1 && neig <= n, "bk_eigen: neig must be in 1..n");
-  DevBuf<double> dA, work, Z;
+  DevBuf<double> dA, Z;
   BK_TRY(h2d(ctx, dA, A, (size_t)n * n));
-  BK_TRY(work.alloc((size_t)n * n));
   if (vecs) BK_TRY(Z.alloc((size_t)n * neig));
   std::vector<double> ev(n);
   int nw = 0;
   // rel_thresh = -inf: keep all neig leading vectors (truncation is the caller's business,
   // R/bigKRLS_Rcpp_functions.R:190)
-  BK_TRY(eigen_full(ctx, dA.p, n, (int)n, work.p, n, ev.data(), vecs ? (int)neig : 0, -INFINITY, &nw,
+  BK_TRY(eigen_full(ctx, dA.p, n, (int)n, ev.data(), vecs ? (int)neig : 0, -INFINITY, &nw,
                     vecs ? Z.p : nullptr, n, nullptr));
   for (int64_t i = 0; i < neig; ++i) vals[i] = ev[i];
   if (vecs) return d2h(ctx, vecs, Z.p, (size_t)n * neig);
@@ -217,13 +216,17 @@ int bk_debug_gemm(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, 
 int bk_debug_sytrd(bk_ctx* ctx, const double* A, int64_t n, double* d, double* e) {
   BK_TRY(enter(ctx, "bk_debug_sytrd"));
   BK_REQUIRE(A && d && e && n > 0 && fits_int(n), "bk_debug_sytrd: bad arguments");
-  DevBuf<double> dA, dd, de, dt;
+  DevBuf<double> dA, dW, dd, de, dt;
+  const long long ldw = sytrd_ld((int)n);
   BK_TRY(h2d(ctx, dA, A, (size_t)n * n));
+  BK_TRY(dW.alloc((size_t)ldw * n));
+  BK_CUDA(cudaMemsetAsync(dW.p, 0, sizeof(double) * (size_t)ldw * n, ctx->stream));
+  BK_TRY(copy_matrix(ctx, dA.p, n, (int)n, (int)n, 1.0, dW.p, ldw));
   BK_TRY(dd.alloc(n));
   BK_TRY(de.alloc(n));
   BK_TRY(dt.alloc(n));
   BK_CUDA(cudaMemsetAsync(de.p, 0, sizeof(double) * n, ctx->stream));
-  BK_TRY(sytrd_lower(ctx, dA.p, n, (int)n, dd.p, de.p, dt.p, 64, nullptr));
+  BK_TRY(sytrd_lower(ctx, dW.p, ldw, (int)n, dd.p, de.p, dt.p, 64, nullptr));
   BK_TRY(d2h(ctx, d, dd.p, n));
   if (n > 1) BK_TRY(d2h(ctx, e, de.p, n - 1));
   return BK_OK;

@@ -138,6 +138,128 @@ __global__ void copy_peak_kernel(const double2* __restrict__ src, double2* __res
     dst[i] = src[i];
 }
 
+// read-only streaming ceilings: (a) plain vector loads, (b) TMA bulk copies into an mbarrier ring
+__global__ void __launch_bounds__(512) read_peak_kernel(const double2* __restrict__ src, long long n2,
+                                                        double* __restrict__ out) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n2; i += 4 * stride) {
+    const double2 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    s0 += a.x + a.y;
+    s1 += b.x + b.y;
+    s2 += c.x + c.y;
+    s3 += d.x + d.y;
+  }
+  for (; i < n2; i += stride) s0 += src[i].x + src[i].y;
+  const double s = s0 + s1 + s2 + s3;
+  if (s == 123.456) out[0] = s;
+}
+
+__device__ __forceinline__ void mb_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 16 consumer warps + 1 producer warp; each stage = 8 x 4 KB bulk copies (32 KB), 5 stages
+__global__ void __launch_bounds__(544, 1) tma_read_peak_kernel(const double* __restrict__ src, long long chunks,
+                                                               double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  double* ring = reinterpret_cast<double*>(dsm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + 5 * 4096);
+  uint64_t* empty = full + 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&empty[i])), "r"(16) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+  unsigned it = 0;
+  double acc = 0.0;
+  if (threadIdx.x == 512) {
+    for (long long c = blockIdx.x; c < chunks; c += gridDim.x, ++it) {
+      const int st = it % 5;
+      mb_wait(&empty[st], ((it / 5) & 1u) ^ 1u);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&full[st])), "r"(32768u) : "memory");
+      for (int k = 0; k < 8; ++k)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         smem_u32(ring + st * 4096 + k * 512)),
+                     "l"(src + c * 4096 + k * 512), "r"(4096u), "r"(smem_u32(&full[st]))
+                     : "memory");
+    }
+  } else if (threadIdx.x < 512) {
+    for (long long c = blockIdx.x; c < chunks; c += gridDim.x, ++it) {
+      const int st = it % 5;
+      mb_wait(&full[st], (it / 5) & 1u);
+      const double* sm = ring + st * 4096 + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += sm[k * 512];
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&empty[st])) : "memory");
+    }
+  }
+  if (acc == 123.456) out[0] = acc;
+}
+
+// strided variant of the TMA ring: the access pattern of the tridiagonalisation SYMV - 8 columns x 512
+// rows per stage, S consecutive row chunks per column before moving to the next 8 columns.
+__global__ void __launch_bounds__(544, 1) tma_strided_peak_kernel(const double* __restrict__ src, int n, long long lda,
+                                                                  int S, double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  double* ring = reinterpret_cast<double*>(dsm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + 5 * 4096);
+  uint64_t* empty = full + 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&empty[i])), "r"(16) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+  const int colblocks = n / 8, rowsegs = n / (512 * S);
+  const long long blocks = (long long)colblocks * rowsegs;
+  unsigned it = 0;
+  double acc = 0.0;
+  if (threadIdx.x == 512) {
+    for (long long b = blockIdx.x; b < blocks; b += gridDim.x) {
+      const long long cbk = b % colblocks, rs = b / colblocks;
+      for (int s = 0; s < S; ++s, ++it) {
+        const int st = it % 5;
+        mb_wait(&empty[st], ((it / 5) & 1u) ^ 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&full[st])), "r"(32768u) : "memory");
+        const double* base = src + (rs * S + s) * 512 + cbk * 8 * lda;
+        for (int k = 0; k < 8; ++k)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                           smem_u32(ring + st * 4096 + k * 512)),
+                       "l"(base + k * lda), "r"(4096u), "r"(smem_u32(&full[st]))
+                       : "memory");
+      }
+    }
+  } else if (threadIdx.x < 512) {
+    for (long long b = blockIdx.x; b < blocks; b += gridDim.x) {
+      for (int s = 0; s < S; ++s, ++it) {
+        const int st = it % 5;
+        mb_wait(&full[st], (it / 5) & 1u);
+        const double* sm = ring + st * 4096 + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += sm[k * 512];
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&empty[st])) : "memory");
+      }
+    }
+  }
+  if (acc == 123.456) out[0] = acc;
+}
+
 __global__ void fill_pattern_kernel(double* p, long long n, unsigned long long seed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -195,6 +317,55 @@ int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result
       const double s = tm.stop();
       BK_CUDA(cudaGetLastError());
       best = fmax(best, 16.0 * (double)n / s * 1e-9);
+    }
+    *result = best;
+    return BK_OK;
+  }
+  if (kind == 3 || kind == 4) {
+    const long long n = (size > 0) ? size : (1LL << 29);  // doubles (4 GiB)
+    bk::DevBuf<double> o;
+    BK_TRY(buf.alloc((size_t)n));
+    BK_TRY(o.alloc(16));
+    bk::fill_pattern_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(buf.p, n, 1);
+    double best = 0.0;
+    if (iters <= 0) iters = 10;
+    const size_t smem = 5 * 32768 + 128;
+    if (kind == 4)
+      BK_CUDA(cudaFuncSetAttribute(bk::tma_read_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rep = 0; rep < iters; ++rep) {
+      tm.start();
+      if (kind == 3)
+        bk::read_peak_kernel<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>((const double2*)buf.p, n / 2, o.p);
+      else
+        bk::tma_read_peak_kernel<<<ctx->sm_count, 544, smem, ctx->stream>>>(buf.p, n / 4096, o.p);
+      BK_LAUNCHED(ctx);
+      const double s = tm.stop();
+      BK_CUDA(cudaGetLastError());
+      best = fmax(best, 8.0 * (double)n / s * 1e-9);
+    }
+    *result = best;
+    return BK_OK;
+  }
+  if (kind == 5) {
+    // size = S (row chunks per column run); matrix 16384 x 16384, lda 16400
+    const int n = 16384;
+    const long long lda = 16400;
+    const int S = (size > 0) ? (int)size : 2;
+    bk::DevBuf<double> o;
+    BK_TRY(buf.alloc((size_t)lda * n));
+    BK_TRY(o.alloc(16));
+    bk::fill_pattern_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(buf.p, lda * n, 1);
+    const size_t smem = 5 * 32768 + 128;
+    BK_CUDA(cudaFuncSetAttribute(bk::tma_strided_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    double best = 0.0;
+    if (iters <= 0) iters = 5;
+    for (int rep = 0; rep < iters; ++rep) {
+      tm.start();
+      bk::tma_strided_peak_kernel<<<ctx->sm_count, 544, smem, ctx->stream>>>(buf.p, n, lda, S, o.p);
+      BK_LAUNCHED(ctx);
+      const double sec = tm.stop();
+      BK_CUDA(cudaGetLastError());
+      best = fmax(best, 8.0 * (double)n * n / sec * 1e-9);
     }
     *result = best;
     return BK_OK;

@@ -40,10 +40,11 @@ struct EigenTimes {
 };
 
 // Full path: K (n x n symmetric, device, preserved) -> evals_host[n] DESCENDING and the
-// eigenvectors selected as in stedc().  `work` is an n x n scratch (destroyed).
-int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work, long long ldw,
-               double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z,
-               long long ldz, EigenTimes* times);
+// eigenvectors selected as in stedc().  Works on an internal copy of K whose leading dimension
+// is padded to a multiple of 16 doubles (aligned columns for the TMA bulk copies of sytrd).
+int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host, int max_want,
+               double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times);
+inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
 
 // Pure host logic of one D&C merge, exported for the CPU unit tests (tests/test_host_logic.py)
 struct MergePlan {

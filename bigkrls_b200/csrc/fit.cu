@@ -249,12 +249,9 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     DevBuf<double> Zfull;
     BK_TRY(Zfull.alloc((size_t)n * f->neig));
     if (!multi || comm->rank == 0) {
-      DevBuf<double> work;
-      BK_TRY(work.alloc((size_t)n * n));
       std::vector<double> ev(n);
       EigenTimes et;
-      BK_TRY(eigen_full(ctx, f->K.p, ld, n, work.p, ld, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p,
-                        ld, &et));
+      BK_TRY(eigen_full(ctx, f->K.p, ld, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et));
       for (int i = 0; i < f->neig; ++i) f->evals[i] = ev[i];
       f->info.t_tridiag = et.tridiag;
       f->info.t_dc = et.dc;

@@ -87,12 +87,15 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
   return BK_OK;
 }
 
-int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* work, long long ldw,
-               double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z,
-               long long ldz, EigenTimes* times) {
+int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host, int max_want,
+               double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times) {
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
-  DevBuf<double> d, e, tau;
+  DevBuf<double> d, e, tau, workbuf;
+  const long long ldw = sytrd_ld(n);
+  BK_TRY(workbuf.alloc((size_t)ldw * n));
+  double* work = workbuf.p;
+  BK_CUDA(cudaMemsetAsync(work, 0, sizeof(double) * (size_t)ldw * n, ctx->stream));
   BK_TRY(d.alloc(n));
   BK_TRY(e.alloc(n));
   BK_TRY(tau.alloc(n));

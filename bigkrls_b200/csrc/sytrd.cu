@@ -3,22 +3,36 @@
 // (reference src/eigen.cpp:24).  Written from the published algorithm (Dongarra/Sorensen/
 // Hammarling blocked reduction: panel of nb reflectors with deferred rank-2nb update).
 //
-// One PERSISTENT COOPERATIVE kernel per panel (all CTAs co-resident, software grid barrier);
-// per column j of the panel:
-//   P1  a = A[j:,j] - V W[j,:]' - W V[j,:]'          rows over all threads, + ||a[j+2:]||^2 partials
-//   P2  Householder (beta, tau, v) computed redundantly by every CTA from the partials
-//   P3  y = A22 v  with A22 the UN-updated trailing matrix: each 64x64 tile of the LOWER
-//       triangle is read ONCE and used for both y_i += T v_j and y_j += T' v_i
-//       (4 m^2 bytes instead of 8 m^2: this read is the HBM roofline of the whole stage);
-//       partial results go to owned slots (no atomics) and are reduced in P4 in a fixed
-//       order => bitwise reproducible.  Also u1 = W'v, u2 = V'v.
-//   P4  w = tau (y - V u1 - W u2),  partials of w.v ;   (next P1)  w += -tau/2 (w.v) v
+// One PERSISTENT COOPERATIVE kernel per panel (one CTA per SM: 16 consumer warps + 1 TMA producer
+// warp, software grid barrier, 3 barriers per column).  Per column j = j0 + c of the panel:
+//
+//   PB  Householder (beta, tau, v) computed redundantly by every CTA from the norm partials
+//       -- barrier --
+//   PC  y = A22 v with A22 the UN-updated trailing matrix.  The lower triangle is cut into
+//       512 x 64 tiles, streamed in 512 x 8 slices by TMA bulk copies (cp.async.bulk, 4 KB
+//       contiguous per column) into a 5-stage mbarrier ring (160 KB in flight per SM) - register
+//       loads could not keep enough bytes in flight to reach the HBM roofline (profiles/);
+//       every element is read from HBM ONCE and used for both y_i += a_ij v_j and
+//       y_j += a_ij v_i (4 m^2 bytes per column instead of 8 m^2 - this read is the HBM roofline
+//       of the whole eigensolver).  Work items are S row tiles x 1 column tile: the transposed
+//       sums stay in registers across the S tile-rows and are reduced over the 512 rows once per
+//       8-column slice (warp reduce-scatter + shared memory); every partial result is written
+//       to an owned slot (no atomics => bitwise reproducible).  Also u1 = W'v, u2 = V'v and the
+//       partials of v'A22v.
+//       -- barrier --
+//   PD  8 threads per row: y = sum of partials, w = tau (y - V u1 - W u2) + alpha v with
+//       alpha = -tau/2 (w.v) obtained from v'A22v and u1.u2 (no extra reduction), then the
+//       SAME threads immediately update the next column a = A[:,j+1] - V W[j+1,:]' - W V[j+1,:]'
+//       and accumulate its norm partials.
+//       -- barrier --
+//
 // After the panel: A22 -= [V W][W V]'  (lower tiles only) on the DMMA GEMM.
 //
 // Layout: A column-major n x n; panel workspace P = [V | W | V] (n x 3nb) so that the rank-2nb
 // update is ONE GEMM  A22 -= P[:,0:2nb] * P[:,nb:3nb]'.  Reflector j is stored LAPACK-style in
 // A[j+2:, j] (v[j+1] = 1 implicit; A[j+1, j] is left holding alpha), e[j] = beta, d[j] = A[j,j].
-#include <cooperative_groups.h>
+//
+// Data written by other CTAs earlier in the same launch is always read through L2 (__ldcg).
 #include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -27,7 +41,18 @@
 
 namespace bk {
 
-static constexpr int TS = 64;  // SYMV tile edge
+static constexpr int TR = 512;    // tile rows  = consumer threads per CTA (one row per thread)
+static constexpr int TC = 64;     // tile columns (8 slices of 8 columns)
+static constexpr int NCONS = 512; // consumer threads (16 warps)
+static constexpr int NTH = 544;   // + 1 producer warp that drives the TMA ring
+static constexpr int NBMAX = 64;  // panel width supported by the shared-memory staging
+static constexpr int NS = 5;      // TMA ring stages
+static constexpr int SLICE = 8;   // columns per stage
+static constexpr int STAGE_DOUBLES = TR * SLICE;  // 512 x 8 doubles = 32 KB per stage
+static constexpr int VCS_MAX = TC;                // v entries of one column tile
+// dynamic shared memory: ring | st[8][16][8] | vcs[256] | full[NS] | empty[NS]
+static constexpr size_t SMEM_BYTES =
+    sizeof(double) * ((size_t)NS * STAGE_DOUBLES + 8 * 16 * 8 + VCS_MAX) + sizeof(uint64_t) * 2 * NS;
 
 struct SytrdArgs {
   double* A;
@@ -37,80 +62,347 @@ struct SytrdArgs {
   double* d;
   double* e;
   double* tau;
-  double* part;    // per-CTA partial sums (2 * gridDim)
-  double* dots;    // 2 * nb + 1: u1 = W'v, u2 = V'v, and w'[j+1] of the current column
-  double* ypart;   // [T][n]   direct partials, owned by (strip bc)
-  double* ytpart;  // [TSEG][n] transposed partials, owned by (segment sb)
+  double* part;    // per-CTA partial sums: [0,G) column norm, [G,2G) v'A22v
+  double* dots;    // 2 * nb: u1 = W'v, u2 = V'v
+  double* ypart;   // [Tc][n]   direct partials, owned by (column tile bc)
+  double* ytpart;  // [NSB][n]  transposed partials, owned by (row segment sb)
   unsigned* barrier;
+  long long* prof;  // optional per-phase cycle counters of CTA 0 (debug)
 };
 
-__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
-// data written by other CTAs earlier in this kernel is always read through L2
-#define LDX(p) __ldcg(p)
+// sum over the 8 lanes of an octet (lanes 8q .. 8q+7); only those lanes need to be converged
+__device__ __forceinline__ double oct_sum(double v) {
+  const unsigned mask = 0xFFu << (threadIdx.x & 24);
+  v += __shfl_xor_sync(mask, v, 1);
+  v += __shfl_xor_sync(mask, v, 2);
+  v += __shfl_xor_sync(mask, v, 4);
+  return v;
+}
 
-__global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
+// Tiling of the trailing matrix of column j.  Tiles are ABSOLUTE (row tiles of 512, column tiles
+// of 64) so that loads stay aligned; rows/columns <= j are neutralised by the zeros of v.
+// A tile is 512 rows x 64 columns: one thread per row, so each column of a tile is a 4 KB
+// contiguous run in memory (DRAM-page friendly) and the direct product needs no cross-thread
+// reduction at all.
+struct ColGeom {
+  int t0r, t0c, Tr, Tc, S, NSB;
+};
+
+__device__ __forceinline__ ColGeom col_geom(int n, int j, int G) {
+  ColGeom g;
+  g.t0r = (j + 1) / TR;
+  g.t0c = (j + 1) / TC;
+  g.Tr = (n + TR - 1) / TR - g.t0r;
+  g.Tc = (n + TC - 1) / TC - g.t0c;
+  // work item = S row tiles x 1 column tile; about half of the Tc x ceil(Tr/S) items carry work and
+  // we want >= ~6 of them per CTA so that the static round-robin assignment stays balanced
+  const long long budget = ((long long)g.Tr * g.Tc) / (12LL * G);
+  g.S = (budget >= 4) ? 4 : (budget >= 2 ? 2 : 1);
+  g.NSB = (g.Tr + g.S - 1) / g.S;
+  return g;
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) -----------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// contiguous global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                             uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS) : "memory"); }
+
+struct ItemGeom {
+  int bc, sb, seg_lo, seg_hi, seg_max_row;
+  bool empty;
+};
+__device__ __forceinline__ ItemGeom item_geom(int n, const ColGeom& g, int item) {
+  ItemGeom it;
+  const int Tr_abs = (n + TR - 1) / TR;
+  it.bc = g.t0c + item % g.Tc;
+  it.sb = item / g.Tc;
+  it.seg_lo = g.t0r + it.sb * g.S;
+  it.seg_hi = min(Tr_abs, it.seg_lo + g.S);
+  it.seg_max_row = it.seg_hi * TR - 1;
+  it.empty = it.seg_max_row < it.bc * TC;  // block entirely above the diagonal
+  return it;
+}
+// A (row tile, 8-column slice) step is streamed iff the tile reaches down to the slice's first column.
+__device__ __forceinline__ bool step_active(const ItemGeom& it, int s, int col0) {
+  return (it.seg_lo + s < it.seg_hi) && ((it.seg_lo + s) * TR + TR - 1 >= col0);
+}
+
+// ---- PC producer: one thread walks the same (item, slice, row tile) sequence as the consumers and
+// keeps the ring full: per step 8 bulk copies of one 4 KB column run each. ------------------------------
+__device__ __forceinline__ void symv_producer(const SytrdArgs& a, const ColGeom& g, int G, double* ring,
+                                              uint64_t* full, uint64_t* empty, unsigned& stage,
+                                              unsigned& parity) {
+  const int n = a.n;
+  const long long lda = a.lda;
+  const int nitems = g.Tc * g.NSB;
+  for (int item = blockIdx.x; item < nitems; item += G) {
+    const ItemGeom it = item_geom(n, g, item);
+    if (it.empty) continue;
+    for (int sl = 0; sl < 8; ++sl) {
+      const int col0 = it.bc * TC + sl * SLICE;
+      const int ncol = max(0, min(SLICE, n - col0));  // slices past the last column carry no bytes
+      for (int s = 0; s < g.S; ++s) {
+        if (!step_active(it, s, col0)) continue;
+        mbar_wait(&empty[stage], parity ^ 1u);
+        const int row0 = (it.seg_lo + s) * TR;
+        const int rows = min(TR, n - row0);
+        const unsigned bytes = (unsigned)(((rows + 1) & ~1) * sizeof(double));  // 16-byte multiple
+        mbar_expect_tx(&full[stage], bytes * (unsigned)ncol);
+        double* dst = ring + (size_t)stage * STAGE_DOUBLES;
+        const double* src = a.A + row0 + (long long)col0 * lda;
+        for (int k = 0; k < ncol; ++k) tma_bulk_g2s(dst + k * TR, src + (long long)k * lda, bytes, &full[stage]);
+        if (++stage == NS) {
+          stage = 0;
+          parity ^= 1u;
+        }
+      }
+    }
+  }
+}
+
+// sum of 8 values over the 32 lanes of a warp by recursive halving (9 exchanges instead of 40):
+// on return lane L holds the warp total of value ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
+__device__ __forceinline__ double warp_reduce_scatter8(const double (&v)[8], int lane) {
+  const bool h1 = lane & 16, h2 = lane & 8, h3 = lane & 4;
+  double w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h1 ? v[i] : v[i + 4], keep = h1 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h2 ? w4[i] : w4[i + 2], keep = h2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const double send = h3 ? w2[0] : w2[1], keep = h3 ? w2[1] : w2[0];
+  double w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  return w1;
+}
+
+// ---- PC consumers: 512 threads, thread = row of the tile ---------------------------------------------------
+template <int S>
+__device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom& g, int G,
+                                              const double* __restrict__ vcol, double& vav,
+                                              const double* ring, uint64_t* full, uint64_t* empty,
+                                              double (*st)[16][8], double* vcs, unsigned& stage,
+                                              unsigned& parity) {
+  const int n = a.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const int nitems = g.Tc * g.NSB;
+  for (int item = blockIdx.x; item < nitems; item += G) {
+    const ItemGeom it = item_geom(n, g, item);
+    if (it.empty) continue;
+    // v of this column tile -> shared (broadcast reads below)
+    consumer_sync();  // previous item's readers of vcs / st are done
+    if (threadIdx.x < TC) {
+      const int col = it.bc * TC + threadIdx.x;
+      vcs[threadIdx.x] = (col < n) ? __ldcg(vcol + col) : 0.0;
+    }
+    double dsum[S], vr[S];
+    int row[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      dsum[s] = 0.0;
+      row[s] = (it.seg_lo + s) * TR + threadIdx.x;
+      vr[s] = (it.seg_lo + s < it.seg_hi && row[s] < n) ? __ldcg(vcol + row[s]) : 0.0;
+    }
+    consumer_sync();
+#pragma unroll 1
+    for (int sl = 0; sl < 8; ++sl) {
+      const int col0 = it.bc * TC + sl * SLICE;
+      double vc[8], accT[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        vc[k] = vcs[sl * SLICE + k];
+        accT[k] = 0.0;
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (!step_active(it, s, col0)) continue;  // uniform
+        mbar_wait(&full[stage], parity);
+        const double* sm = ring + (size_t)stage * STAGE_DOUBLES + threadIdx.x;
+        double av[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) av[k] = sm[k * TR];
+        double t = 0.0;
+        if ((it.seg_lo + s) * TR > col0 + 7) {
+          // strictly below the diagonal
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            t = fma(av[k], vc[k], t);
+            accT[k] = fma(av[k], vr[s], accT[k]);
+          }
+        } else {
+          // tile touches the diagonal: lower triangle only
+          const int r = row[s];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (r >= col0 + k) t = fma(av[k], vc[k], t);                 // includes the diagonal once
+            if (r > col0 + k) accT[k] = fma(av[k], vr[s], accT[k]);      // strictly lower only
+          }
+        }
+        dsum[s] += t;
+        vav = fma(vr[s], t, vav);
+        // the values have been consumed (so the shared-memory reads are complete): hand the
+        // stage back to the TMA producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == NS) {
+          stage = 0;
+          parity ^= 1u;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vav = fma(vc[k], accT[k], vav);
+      const double tot = warp_reduce_scatter8(accT, lane);
+      if ((lane & 3) == 0) st[sl][warp][ridx] = tot;
+    }
+    // transposed sums of this column tile: fixed-order sum over the 16 warps, one owned slot
+    consumer_sync();
+    if (threadIdx.x < TC) {
+      const int col = it.bc * TC + threadIdx.x;
+      if (col < n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) acc += st[threadIdx.x >> 3][w][threadIdx.x & 7];
+        a.ytpart[(size_t)it.sb * n + col] = acc;
+      }
+    }
+    // direct sums: one thread per row, nothing to reduce - one owned slot per (column tile, row)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int br = it.seg_lo + s;
+      if (br < it.seg_hi && br * 8 + 7 >= it.bc && row[s] < n)
+        a.ypart[(size_t)(it.bc - g.t0c) * n + row[s]] = dsum[s];
+    }
+  }
+}
+
+// ---- PD helper: final w of row r, computed by the 8 lanes of an octet (all return the same value) ---------
+__device__ __forceinline__ double final_w(const SytrdArgs& a, const ColGeom& g, int r, int sub, int c,
+                                          const double* V, const double* W, const double* vcol,
+                                          const double* u1, const double* u2, double tau,
+                                          double alpha) {
+  const int n = a.n;
+  double acc = 0.0;
+  const int ncb = min(g.Tc, (r / TR) * 8 + 7 - g.t0c + 1);
+  for (int i = sub; i < ncb; i += 8) acc += __ldcg(a.ypart + (size_t)i * n + r);
+  const int sb_min = ((r / TC) / 8 - g.t0r) / g.S;
+  for (int i = sb_min + sub; i < g.NSB; i += 8) acc += __ldcg(a.ytpart + (size_t)i * n + r);
+  for (int q = sub; q < c; q += 8)
+    acc -= __ldcg(V + (size_t)q * n + r) * u1[q] + __ldcg(W + (size_t)q * n + r) * u2[q];
+  acc = oct_sum(acc);
+  return tau * acc + alpha * __ldcg(vcol + r);
+}
+
+__global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
   __shared__ double red[32];
-  __shared__ double sd[2][4][TS];
-  __shared__ double st[4][16][2];
+  __shared__ double s_u1[NBMAX], s_u2[NBMAX], s_wrow[NBMAX + 1], s_vrow[NBMAX + 1];
+  __shared__ double s_scal[2];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  double* ring = reinterpret_cast<double*>(dyn_smem);                       // NS x 8 x 512
+  double(*st)[16][8] = reinterpret_cast<double(*)[16][8]>(ring + (size_t)NS * STAGE_DOUBLES);
+  double* vcs = ring + (size_t)NS * STAGE_DOUBLES + 8 * 16 * 8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(vcs + VCS_MAX);
+  uint64_t* empty = full + NS;
+  unsigned stage = 0, parity = 0;  // ring position (same sequence in the producer and every consumer)
   const int n = a.n, nb = a.nb;
-  double* __restrict__ A = a.A;
+  double* A = a.A;
   const long long lda = a.lda;
   double* V = a.P;
   double* W = a.P + (size_t)nb * n;
   double* V2 = a.P + (size_t)2 * nb * n;
   const int G = gridDim.x;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int gthreads = G * blockDim.x;
+  const int gid = blockIdx.x * NTH + threadIdx.x;
+  const int gthreads = G * NTH;
+  const int oct = gid >> 3, sub = gid & 7, nocts = gthreads >> 3;  // PD: 8 lanes per row
   unsigned epoch = 0;
-  const int T = (n + TS - 1) / TS;
+  // ring: zero (stale-but-finite data is multiplied by v = 0 at the matrix edge), barriers, fences
+  for (int i = threadIdx.x; i < NS * STAGE_DOUBLES; i += NTH) ring[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NCONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+  long long tprev = clock64();
+#define PROF(slot)                                                   \
+  do {                                                               \
+    if (a.prof && gid == 0) {                                        \
+      const long long tnow = clock64();                              \
+      a.prof[slot] += tnow - tprev;                                  \
+      tprev = tnow;                                                  \
+    }                                                                \
+  } while (0)
 
-  double alpha_prev = 0.0;  // -tau/2 (w.v) of the previous column, applied lazily
-  int pending = -1;         // panel column whose w still lacks the alpha*v correction
-  for (int c = 0; c < nb; ++c) {
-    const int j = a.j0 + c;
-    if (j >= n) break;
-    // ---------------- P1: finish previous w, update column j ----------------------------------
-    // previous column's w: W[r, c-1] += alpha_prev * V[r, c-1]   (rows r > j-1, i.e. r >= j)
-    // W[j, c-1] after the correction is needed by every thread: w'[j] was parked in
-    // dots[2nb] by P4 (V[j, c-1] == 1), so nobody reads the element another thread rewrites.
-    double wjc = 0.0;
-    if (c > 0) wjc = ldcg(a.dots + 2 * nb) + alpha_prev;
-    pending = -1;
+  // ---- prologue: column j0 needs no update inside this panel: d and the norm partials -------------------
+  {
+    const int j = a.j0;
     double ss = 0.0;
     for (int r = j + gid; r < n; r += gthreads) {
-      if (c > 0) {
-        double* wp = W + (size_t)(c - 1) * n;
-        wp[r] = LDX(wp + r) + alpha_prev * LDX(V + (size_t)(c - 1) * n + r);
-      }
-      double v = A[r + (long long)j * lda];
-      for (int q = 0; q < c; ++q) {
-        const double wjq = (q == c - 1) ? wjc : ldcg(W + (size_t)q * n + j);
-        const double vjq = ldcg(V + (size_t)q * n + j);
-        v -= LDX(V + (size_t)q * n + r) * wjq + LDX(W + (size_t)q * n + r) * vjq;
-      }
-      A[r + (long long)j * lda] = v;
+      const double v = A[r + (long long)j * lda];
       if (r == j) a.d[j] = v;
       if (r > j + 1) ss += v * v;
     }
-    if (j == n - 1) break;  // last diagonal element: nothing to reflect
     ss = block_sum(ss, red);
     if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
     grid_barrier(a.barrier, epoch);
+  }
 
-    // ---------------- P2: Householder vector ------------------------------------------------
+  for (int c = 0; c < nb; ++c) {
+    const int j = a.j0 + c;
+    if (j >= n - 1) break;  // the last diagonal element has no reflector
+    // ---------------- PB: Householder vector ------------------------------------------------
     double xnorm2 = 0.0;  // same fixed-shape reduction in every CTA => identical value everywhere
-    for (int b = threadIdx.x; b < G; b += blockDim.x) xnorm2 += ldcg(a.part + b);
+    for (int b = threadIdx.x; b < G; b += NTH) xnorm2 += __ldcg(a.part + b);
     xnorm2 = block_sum(xnorm2, red);
-    const double alpha = ldcg(A + (j + 1) + (long long)j * lda);
+    const double alpha0 = __ldcg(A + (j + 1) + (long long)j * lda);
     double beta, tau, scale;
     if (xnorm2 == 0.0) {
-      beta = alpha;
+      beta = alpha0;
       tau = 0.0;
       scale = 0.0;
     } else {
-      beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
+      beta = -copysign(sqrt(alpha0 * alpha0 + xnorm2), alpha0);
+      tau = (beta - alpha0) / beta;
+      scale = 1.0 / (alpha0 - beta);
     }
     if (gid == 0) {
       a.e[j] = beta;
@@ -123,126 +415,105 @@ __global__ void __launch_bounds__(256, 2) sytrd_panel_kernel(SytrdArgs a) {
         // overwritten here (beta lives in e[j]; the back-transform uses an explicit 1).
         v = 1.0;
       } else {
-        v = ldcg(A + r + (long long)j * lda) * scale;
+        v = __ldcg(A + r + (long long)j * lda) * scale;
         A[r + (long long)j * lda] = v;
       }
       V[(size_t)c * n + r] = v;
       V2[(size_t)c * n + r] = v;
     }
+    PROF(0);
     grid_barrier(a.barrier, epoch);
+    PROF(1);
 
     const double* vcol = V + (size_t)c * n;
-    // ---------------- P3: u = [W V]'v  and  y = A22 v ------------------------------------------
+    const ColGeom g = col_geom(n, j, G);
+    // ---------------- PC: u = [W V]'v,  y = A22 v,  v'A22v ---------------------------------------------
     for (int q = blockIdx.x; q < 2 * c; q += G) {
       const double* col = (q < c) ? (W + (size_t)q * n) : (V + (size_t)(q - c) * n);
       double s = 0.0;
-      for (int r = j + 1 + threadIdx.x; r < n; r += blockDim.x) s += LDX(col + r) * ldcg(vcol + r);
+      for (int r = j + 1 + threadIdx.x; r < n; r += NTH) s += __ldcg(col + r) * __ldcg(vcol + r);
       s = block_sum(s, red);
       if (threadIdx.x == 0) a.dots[(q < c) ? q : (nb + q - c)] = s;
     }
+    PROF(2);
     {
-      const int t0 = (j + 1) / TS;            // first tile row/col touching the trailing matrix
-      const int Tm = T - t0;                  // tiles per side
-      int S = (int)(((long long)Tm * Tm) / (8LL * G));
-      S = max(1, min(8, S));
-      const int NSEG = (Tm + S - 1) / S;
-      const int rr = threadIdx.x & (TS - 1), cg = threadIdx.x >> 6;  // row in tile, column group
-      const int lane = threadIdx.x & 31;
-      for (int item = blockIdx.x; item < Tm * NSEG; item += G) {
-        const int bc = t0 + item % Tm, sb = item / Tm;
-        const int br_lo = max(bc, t0 + sb * S), br_hi = min(T, t0 + sb * S + S);
-        if (br_lo >= br_hi) continue;  // uniform per CTA
-        const int col0 = bc * TS + cg * 16;
-        double vc[16], accT[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          vc[k] = (col0 + k < n) ? ldcg(vcol + col0 + k) : 0.0;
-          accT[k] = 0.0;
-        }
-        int parity = 0;
-        for (int br = br_lo; br < br_hi; ++br) {
-          const int row = br * TS + rr;
-          const bool rok = row < n;
-          const double vr = rok ? ldcg(vcol + row) : 0.0;
-          const double* ap = A + row + (long long)col0 * lda;
-          double av[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) av[k] = (rok && col0 + k < n) ? ap[(long long)k * lda] : 0.0;
-          double dsum = 0.0;
-          if (br != bc) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              dsum = fma(av[k], vc[k], dsum);
-              accT[k] = fma(av[k], vr, accT[k]);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int col = col0 + k;
-              if (row > col) {
-                dsum = fma(av[k], vc[k], dsum);
-                accT[k] = fma(av[k], vr, accT[k]);
-              } else if (row == col) {
-                dsum = fma(av[k], vc[k], dsum);
-              }
-            }
-          }
-          sd[parity][cg][rr] = dsum;
-          __syncthreads();
-          if (threadIdx.x < TS) {
-            const double s = (sd[parity][0][rr] + sd[parity][1][rr]) +
-                             (sd[parity][2][rr] + sd[parity][3][rr]);
-            if (row < n) a.ypart[(size_t)bc * n + row] = s;
-          }
-          parity ^= 1;
-        }
-        // transposed partials: reduce accT over the 64 rows (2 warps per column group)
-#pragma unroll
-        for (int k = 0; k < 16; ++k) accT[k] = warp_sum(accT[k]);
-        __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) st[cg][k][(threadIdx.x >> 5) & 1] = accT[k];
-        }
-        __syncthreads();
-        if (threadIdx.x < 64) {
-          const int g4 = threadIdx.x >> 4, k = threadIdx.x & 15;
-          const int col = bc * TS + g4 * 16 + k;
-          if (col < n) a.ytpart[(size_t)sb * n + col] = st[g4][k][0] + st[g4][k][1];
-        }
-        __syncthreads();
+      double vav = 0.0;
+      if (threadIdx.x < NCONS) {
+        if (g.S == 4)
+          symv_consumer<4>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+        else if (g.S == 2)
+          symv_consumer<2>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+        else
+          symv_consumer<1>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+      } else if (threadIdx.x == NCONS) {
+        symv_producer(a, g, G, ring, full, empty, stage, parity);
       }
-      grid_barrier(a.barrier, epoch);
-
-      // -------------- P4: w = tau (y - V u1 - W u2), partial w.v ------------------------------
-      double wv = 0.0;
-      for (int r = j + 1 + gid; r < n; r += gthreads) {
-        const int br = r / TS;
-        double y = 0.0;
-        for (int bcx = t0; bcx <= br; ++bcx) y += ldcg(a.ypart + (size_t)bcx * n + r);
-        for (int sbx = (br - t0) / S; sbx < NSEG; ++sbx) y += ldcg(a.ytpart + (size_t)sbx * n + r);
-        for (int q = 0; q < c; ++q)
-          y -= LDX(V + (size_t)q * n + r) * ldcg(a.dots + q) + LDX(W + (size_t)q * n + r) * ldcg(a.dots + nb + q);
-        const double w = tau * y;
-        W[(size_t)c * n + r] = w;
-        if (r == j + 1) a.dots[2 * nb] = w;
-        wv += w * ldcg(vcol + r);
-      }
-      wv = block_sum(wv, red);
-      if (threadIdx.x == 0) a.part[G + blockIdx.x] = wv;
-      grid_barrier(a.barrier, epoch);
-      double tot = 0.0;
-      for (int b = threadIdx.x; b < G; b += blockDim.x) tot += ldcg(a.part + G + b);
-      tot = block_sum(tot, red);
-      alpha_prev = -0.5 * tau * tot;
-      pending = c;
+      stage = __shfl_sync(0xffffffffu, stage, 0);  // producer warp: lanes follow lane 0
+      parity = __shfl_sync(0xffffffffu, parity, 0);
+      vav = block_sum(vav, red);
+      if (threadIdx.x == 0) a.part[G + blockIdx.x] = vav;
     }
-  }
-  // finish the last w of the panel
-  if (pending >= 0) {
-    const int c = pending, j = a.j0 + c;
-    for (int r = j + 1 + gid; r < n; r += gthreads)
-      W[(size_t)c * n + r] += alpha_prev * V[(size_t)c * n + r];
+    PROF(3);
+    grid_barrier(a.barrier, epoch);
+    PROF(4);
+
+    // ---------------- PD: w (final) for own rows, then the next column's update -------------------------
+    {
+      double vav = 0.0;
+      for (int b = threadIdx.x; b < G; b += NTH) vav += __ldcg(a.part + G + b);
+      vav = block_sum(vav, red);
+      for (int q = threadIdx.x; q < c; q += NTH) {
+        s_u1[q] = __ldcg(a.dots + q);
+        s_u2[q] = __ldcg(a.dots + nb + q);
+        s_wrow[q] = __ldcg(W + (size_t)q * n + (j + 1));
+        s_vrow[q] = __ldcg(V + (size_t)q * n + (j + 1));
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double uu = 0.0;
+        for (int q = 0; q < c; ++q) uu = fma(s_u1[q], s_u2[q], uu);
+        // w.v = tau (v'A22v - 2 u1.u2)  =>  alpha = -tau/2 (w.v)
+        s_scal[0] = -0.5 * tau * (tau * (vav - 2.0 * uu));
+      }
+      __syncthreads();
+      const double alpha = s_scal[0];
+      // W[j+1, c] is needed by every thread for the next column: each CTA recomputes it with the
+      // owner's exact procedure (same octet split, same order) so the value is bitwise identical.
+      if (threadIdx.x < 8) {
+        const double wj1 = final_w(a, g, j + 1, threadIdx.x, c, V, W, vcol, s_u1, s_u2, tau, alpha);
+        if (threadIdx.x == 0) {
+          s_wrow[c] = wj1;
+          s_vrow[c] = 1.0;
+        }
+      }
+      __syncthreads();
+      const bool next = (c + 1 < nb);  // the next panel's prologue handles its own first column
+      const int jn = j + 1;
+      double ss = 0.0;
+      for (int r = j + 1 + oct; r < n; r += nocts) {
+        const double w = final_w(a, g, r, sub, c, V, W, vcol, s_u1, s_u2, tau, alpha);
+        if (sub == 0) W[(size_t)c * n + r] = w;
+        if (next) {
+          double acc = (sub == 0) ? A[r + (long long)jn * lda] : 0.0;
+          for (int q = sub; q < c; q += 8)
+            acc -= __ldcg(V + (size_t)q * n + r) * s_wrow[q] + __ldcg(W + (size_t)q * n + r) * s_vrow[q];
+          if (sub == (c & 7)) acc -= __ldcg(vcol + r) * s_wrow[c] + w * s_vrow[c];
+          acc = oct_sum(acc);
+          if (sub == 0) {
+            A[r + (long long)jn * lda] = acc;
+            if (r == jn) a.d[jn] = acc;
+            if (r > jn + 1) ss += acc * acc;
+          }
+        }
+      }
+      PROF(5);
+      if (next) {
+        ss = block_sum(ss, red);
+        if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
+        grid_barrier(a.barrier, epoch);
+      }
+      PROF(6);
+    }
   }
 }
 
@@ -253,21 +524,28 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     BK_CUDA(cudaMemcpyAsync(d, A, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return BK_OK;
   }
+  BK_REQUIRE(nb >= 1 && nb <= NBMAX, "sytrd: panel width must be in 1..%d", NBMAX);
   int occ = 0;
-  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel, 256, 0));
+  BK_REQUIRE(lda % 2 == 0, "sytrd: leading dimension must be even (16-byte aligned columns for TMA)");
+  BK_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)SMEM_BYTES));
+  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel, NTH, SMEM_BYTES));
   BK_REQUIRE(occ >= 1, "sytrd: kernel does not fit on an SM");
-  occ = std::min(occ, 2);
-  if (const char* ev = getenv("BK_SYTRD_OCC")) occ = std::max(1, std::min(occ, atoi(ev)));
-  const int G = ctx->sm_count * occ;
-  const int T = (int)ceil_div(n, TS);
-  const int TSEG = T;  // upper bound on the number of row segments (S >= 1)
+  const int G = ctx->sm_count;  // one CTA per SM
+  const int T = (int)ceil_div(n, TC);
   DevBuf<double> P, part, dots, ypart, ytpart;
   BK_TRY(P.alloc((size_t)3 * nb * n));
   BK_TRY(part.alloc((size_t)2 * G));
-  BK_TRY(dots.alloc((size_t)2 * nb + 1));
-  BK_TRY(ypart.alloc((size_t)T * n));
-  BK_TRY(ytpart.alloc((size_t)TSEG * n));
+  BK_TRY(dots.alloc((size_t)2 * nb));
+  BK_TRY(ypart.alloc((size_t)T * n));   // Tc <= T
+  BK_TRY(ytpart.alloc((size_t)T * n));  // NSB <= T
   BK_TRY(ctx->barrier.ensure(4));
+  DevBuf<long long> prof;
+  const bool do_prof = getenv("BK_SYTRD_PROF") != nullptr;
+  if (do_prof) {
+    BK_TRY(prof.alloc(8));
+    BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+  }
 
   // per-panel CUDA events on the launching stream: the roofline numbers of bench.py are the
   // sum of these kernel durations against the algorithmic bytes 4 m_j^2 per column
@@ -294,9 +572,10 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     args.ypart = ypart.p;
     args.ytpart = ytpart.p;
     args.barrier = ctx->barrier.p;
+    args.prof = prof.p;
     void* kargs[] = {&args};
     if (stats) BK_CUDA(cudaEventRecord(ev0[pi], ctx->stream));
-    BK_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(G), dim3(256), kargs, 0,
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(G), dim3(NTH), kargs, SMEM_BYTES,
                                         ctx->stream));
     if (stats) BK_CUDA(cudaEventRecord(ev1[pi], ctx->stream));
     BK_LAUNCHED(ctx);
@@ -309,6 +588,16 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     }
   }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));  // workspaces are freed on return
+  if (do_prof) {
+    long long h[8];
+    BK_CUDA(cudaMemcpy(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const char* names[7] = {"PB", "wait(B2)", "PC dots", "PC symv", "wait(B3)", "PD", "wait(B1)"};
+    long long tot = 0;
+    for (int i = 0; i < 7; ++i) tot += h[i];
+    fprintf(stderr, "[sytrd prof n=%d] CTA0 cycles:", n);
+    for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (double)tot);
+    fprintf(stderr, " total=%.3f Gcyc\n", tot * 1e-9);
+  }
   if (stats) {
     stats->launches = npanels;
     stats->kernel_seconds = 0.0;

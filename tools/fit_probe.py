@@ -15,8 +15,9 @@ N, P = int(sys.argv[1]), int(sys.argv[2])
 kw = {}
 if len(sys.argv) > 3:
     kw["eigtrunc"] = float(sys.argv[3])
-X, y = o.synthetic(N, P, 1000 + P)
-for rep in range(2):
+reps = 1 if (len(sys.argv) > 4 and sys.argv[4] == "once") else 2
+X, y = o.synthetic(N, P, 1003 if (N, P) == (20000, 10) else 1000 + P)
+for rep in range(reps):
     t0 = time.time()
     fit = bigKRLS(y, X, return_squares=False, **kw)
     t1 = time.time()

@@ -12,9 +12,13 @@ lib = _lib.load()
 ctx = _lib.default_context(0)
 out = {"device": ctx.device_info()}
 r = C.c_double()
-for kind, name in ((0, "dfma_tflops"), (1, "dmma_tflops"), (2, "hbm_copy_gbs")):
+for kind, name in ((0, "dfma_tflops"), (1, "dmma_tflops"), (2, "hbm_copy_gbs"), (3, "hbm_read_ldg_gbs"),
+                   (4, "hbm_read_tma_ring_gbs")):
     _lib.check(lib.bk_microbench(ctx.handle, kind, 0, 0, C.byref(r)))
     out[name] = r.value
+if "--peaks-only" in sys.argv:
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 shapes = [(0, 1, 8192, 8192, 8192, 0), (0, 0, 8192, 8192, 8192, 0), (1, 0, 8192, 8192, 8192, 0),
           (0, 1, 16384, 16384, 2048, 1), (0, 1, 16384, 16384, 128, 1), (0, 0, 20000, 22, 20000, 0),
           (1, 0, 2000, 10, 20000, 0), (0, 0, 16384, 2048, 64, 0), (1, 0, 64, 2048, 16384, 0)]
