@@ -46,6 +46,7 @@ static constexpr int TC = 64;     // tile columns (8 slices of 8 columns)
 static constexpr int NCONS = 512; // consumer threads (16 warps)
 static constexpr int NTH = 544;   // + 1 producer warp that drives the TMA ring
 static constexpr int NBMAX = 64;  // panel width supported by the shared-memory staging
+static constexpr int SEGMAX = 256; // max row segments per column (n <= 131072)
 static constexpr int NS = 5;      // TMA ring stages
 static constexpr int SLICE = 8;   // columns per stage
 static constexpr int STAGE_DOUBLES = TR * SLICE;  // 512 x 8 doubles = 32 KB per stage
@@ -64,7 +65,7 @@ struct SytrdArgs {
   double* tau;
   double* part;    // per-CTA partial sums: [0,G) column norm, [G,2G) v'A22v
   double* dots;    // 2 * nb: u1 = W'v, u2 = V'v
-  double* ypart;   // [Tc][n]   direct partials, owned by (column tile bc)
+  double* ypart;   // [G][n]    direct partials, owned by (CTA, row)
   double* ytpart;  // [NSB][n]  transposed partials, owned by (row segment sb)
   unsigned* barrier;
   long long* prof;  // optional per-phase cycle counters of CTA 0 (debug)
@@ -137,21 +138,59 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS) : "memory"); }
 
+// Work items: (row segment sb of S row tiles) x (one column tile bc), only those that reach below the
+// diagonal.  They are enumerated sb-major / bc-minor and CTA b takes the CONTIGUOUS range
+// [b M / G, (b+1) M / G): perfectly balanced, and consecutive items of a CTA share the row segment, so
+// the direct sums stay in registers across them and a row receives one partial per CTA that touched
+// its segment (~M/G column tiles each) instead of one per column tile.
+__device__ __forceinline__ int seg_count(int n, const ColGeom& g, int sb) {
+  const int Tr_abs = (n + TR - 1) / TR, Tc_abs = (n + TC - 1) / TC;
+  const int seg_hi = min(Tr_abs, g.t0r + sb * g.S + g.S);
+  const int max_bc = min(Tc_abs - 1, (seg_hi * TR - 1) / TC);
+  return max_bc - g.t0c + 1;  // >= 1
+}
+__device__ __forceinline__ long long range_start(long long M, int G, int b) { return (M * b) / G; }
+
 struct ItemGeom {
-  int bc, sb, seg_lo, seg_hi, seg_max_row;
-  bool empty;
+  int bc, sb, seg_lo, seg_hi;
 };
-__device__ __forceinline__ ItemGeom item_geom(int n, const ColGeom& g, int item) {
+__device__ __forceinline__ ItemGeom item_geom(int n, const ColGeom& g, int sb, int bc) {
   ItemGeom it;
   const int Tr_abs = (n + TR - 1) / TR;
-  it.bc = g.t0c + item % g.Tc;
-  it.sb = item / g.Tc;
-  it.seg_lo = g.t0r + it.sb * g.S;
+  it.bc = bc;
+  it.sb = sb;
+  it.seg_lo = g.t0r + sb * g.S;
   it.seg_hi = min(Tr_abs, it.seg_lo + g.S);
-  it.seg_max_row = it.seg_hi * TR - 1;
-  it.empty = it.seg_max_row < it.bc * TC;  // block entirely above the diagonal
   return it;
 }
+// iterator over the items of this CTA (identical in the producer and in every consumer)
+struct ItemIter {
+  int sb, bc, left_in_seg;
+  long long left;
+  __device__ __forceinline__ void init(int n, const ColGeom& g, long long M, int G, int b) {
+    const long long lo = range_start(M, G, b), hi = range_start(M, G, b + 1);
+    left = hi - lo;
+    sb = 0;
+    long long off = 0;
+    int cnt = seg_count(n, g, 0);
+    while (left > 0 && off + cnt <= lo) {
+      off += cnt;
+      ++sb;
+      cnt = seg_count(n, g, sb);
+    }
+    bc = g.t0c + (int)(lo - off);
+    left_in_seg = cnt - (int)(lo - off);
+  }
+  __device__ __forceinline__ void advance(int n, const ColGeom& g) {
+    --left;
+    ++bc;
+    if (--left_in_seg == 0 && left > 0) {
+      ++sb;
+      bc = g.t0c;
+      left_in_seg = seg_count(n, g, sb);
+    }
+  }
+};
 // A (row tile, 8-column slice) step is streamed iff the tile reaches down to the slice's first column.
 __device__ __forceinline__ bool step_active(const ItemGeom& it, int s, int col0) {
   return (it.seg_lo + s < it.seg_hi) && ((it.seg_lo + s) * TR + TR - 1 >= col0);
@@ -159,15 +198,15 @@ __device__ __forceinline__ bool step_active(const ItemGeom& it, int s, int col0)
 
 // ---- PC producer: one thread walks the same (item, slice, row tile) sequence as the consumers and
 // keeps the ring full: per step 8 bulk copies of one 4 KB column run each. ------------------------------
-__device__ __forceinline__ void symv_producer(const SytrdArgs& a, const ColGeom& g, int G, double* ring,
-                                              uint64_t* full, uint64_t* empty, unsigned& stage,
-                                              unsigned& parity) {
+__device__ __forceinline__ void symv_producer(const SytrdArgs& a, const ColGeom& g, long long M, int G,
+                                              double* ring, uint64_t* full, uint64_t* empty,
+                                              unsigned& stage, unsigned& parity) {
   const int n = a.n;
   const long long lda = a.lda;
-  const int nitems = g.Tc * g.NSB;
-  for (int item = blockIdx.x; item < nitems; item += G) {
-    const ItemGeom it = item_geom(n, g, item);
-    if (it.empty) continue;
+  ItemIter iter;
+  iter.init(n, g, M, G, blockIdx.x);
+  for (; iter.left > 0; iter.advance(n, g)) {
+    const ItemGeom it = item_geom(n, g, iter.sb, iter.bc);
     for (int sl = 0; sl < 8; ++sl) {
       const int col0 = it.bc * TC + sl * SLICE;
       const int ncol = max(0, min(SLICE, n - col0));  // slices past the last column carry no bytes
@@ -214,7 +253,7 @@ __device__ __forceinline__ double warp_reduce_scatter8(const double (&v)[8], int
 
 // ---- PC consumers: 512 threads, thread = row of the tile ---------------------------------------------------
 template <int S>
-__device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom& g, int G,
+__device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom& g, long long M, int G,
                                               const double* __restrict__ vcol, double& vav,
                                               const double* ring, uint64_t* full, uint64_t* empty,
                                               double (*st)[16][8], double* vcs, unsigned& stage,
@@ -222,23 +261,44 @@ __device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom&
   const int n = a.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const int nitems = g.Tc * g.NSB;
-  for (int item = blockIdx.x; item < nitems; item += G) {
-    const ItemGeom it = item_geom(n, g, item);
-    if (it.empty) continue;
-    // v of this column tile -> shared (broadcast reads below)
+  ItemIter iter;
+  iter.init(n, g, M, G, blockIdx.x);
+  int cur_sb = -1;
+  double dsum[S], vr[S];
+  int row[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    dsum[s] = 0.0;
+    vr[s] = 0.0;
+    row[s] = 0;
+  }
+  // direct sums of the finished row segment: one thread per row, nothing to reduce; one owned slot
+  // per (CTA, row)
+  auto flush = [&]() {
+    if (cur_sb < 0) return;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (row[s] < n && row[s] / TR - g.t0r < (cur_sb + 1) * g.S)
+        a.ypart[(size_t)blockIdx.x * n + row[s]] = dsum[s];
+      dsum[s] = 0.0;
+    }
+  };
+  for (; iter.left > 0; iter.advance(n, g)) {
+    const ItemGeom it = item_geom(n, g, iter.sb, iter.bc);
     consumer_sync();  // previous item's readers of vcs / st are done
     if (threadIdx.x < TC) {
       const int col = it.bc * TC + threadIdx.x;
       vcs[threadIdx.x] = (col < n) ? __ldcg(vcol + col) : 0.0;
     }
-    double dsum[S], vr[S];
-    int row[S];
+    if (it.sb != cur_sb) {
+      flush();
+      cur_sb = it.sb;
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      dsum[s] = 0.0;
-      row[s] = (it.seg_lo + s) * TR + threadIdx.x;
-      vr[s] = (it.seg_lo + s < it.seg_hi && row[s] < n) ? __ldcg(vcol + row[s]) : 0.0;
+      for (int s = 0; s < S; ++s) {
+        row[s] = (it.seg_lo + s) * TR + threadIdx.x;
+        vr[s] = (it.seg_lo + s < it.seg_hi && row[s] < n) ? __ldcg(vcol + row[s]) : 0.0;
+        if (it.seg_lo + s >= it.seg_hi) row[s] = n;  // tile row beyond the matrix: never stored
+      }
     }
     consumer_sync();
 #pragma unroll 1
@@ -268,7 +328,7 @@ __device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom&
           }
         } else {
           // tile touches the diagonal: lower triangle only
-          const int r = row[s];
+          const int r = (it.seg_lo + s) * TR + threadIdx.x;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             if (r >= col0 + k) t = fma(av[k], vc[k], t);                 // includes the diagonal once
@@ -302,25 +362,23 @@ __device__ __forceinline__ void symv_consumer(const SytrdArgs& a, const ColGeom&
         a.ytpart[(size_t)it.sb * n + col] = acc;
       }
     }
-    // direct sums: one thread per row, nothing to reduce - one owned slot per (column tile, row)
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int br = it.seg_lo + s;
-      if (br < it.seg_hi && br * 8 + 7 >= it.bc && row[s] < n)
-        a.ypart[(size_t)(it.bc - g.t0c) * n + row[s]] = dsum[s];
-    }
   }
+  flush();
 }
 
 // ---- PD helper: final w of row r, computed by the 8 lanes of an octet (all return the same value) ---------
-__device__ __forceinline__ double final_w(const SytrdArgs& a, const ColGeom& g, int r, int sub, int c,
-                                          const double* V, const double* W, const double* vcol,
-                                          const double* u1, const double* u2, double tau,
-                                          double alpha) {
+__device__ __forceinline__ double final_w(const SytrdArgs& a, const ColGeom& g, long long M, int G,
+                                          const int* s_off, int r, int sub, int c, const double* V,
+                                          const double* W, const double* vcol, const double* u1,
+                                          const double* u2, double tau, double alpha) {
   const int n = a.n;
   double acc = 0.0;
-  const int ncb = min(g.Tc, (r / TR) * 8 + 7 - g.t0c + 1);
-  for (int i = sub; i < ncb; i += 8) acc += __ldcg(a.ypart + (size_t)i * n + r);
+  // CTAs whose item range intersects this row's segment (s_off: prefix sums of the segment sizes)
+  const int sbr = (r / TR - g.t0r) / g.S;
+  const long long o1 = s_off[sbr], o2 = s_off[sbr + 1] - 1;
+  const int b_lo = (int)(((o1 + 1) * G + M - 1) / M) - 1, b_hi = (int)(((o2 + 1) * G + M - 1) / M) - 1;
+  for (int b = b_lo + sub; b <= b_hi; b += 8)
+    if (range_start(M, G, b + 1) > range_start(M, G, b)) acc += __ldcg(a.ypart + (size_t)b * n + r);
   const int sb_min = ((r / TC) / 8 - g.t0r) / g.S;
   for (int i = sb_min + sub; i < g.NSB; i += 8) acc += __ldcg(a.ytpart + (size_t)i * n + r);
   for (int q = sub; q < c; q += 8)
@@ -333,6 +391,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
   __shared__ double red[32];
   __shared__ double s_u1[NBMAX], s_u2[NBMAX], s_wrow[NBMAX + 1], s_vrow[NBMAX + 1];
   __shared__ double s_scal[2];
+  __shared__ int s_off[SEGMAX + 1];
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   double* ring = reinterpret_cast<double*>(dyn_smem);                       // NS x 8 x 512
   double(*st)[16][8] = reinterpret_cast<double(*)[16][8]>(ring + (size_t)NS * STAGE_DOUBLES);
@@ -427,6 +486,17 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
 
     const double* vcol = V + (size_t)c * n;
     const ColGeom g = col_geom(n, j, G);
+    // prefix sums of the per-segment item counts (needed by PD; M = total number of items)
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int sb = 0; sb < g.NSB; ++sb) {
+        s_off[sb] = acc;
+        acc += seg_count(n, g, sb);
+      }
+      s_off[g.NSB] = acc;
+    }
+    __syncthreads();
+    const long long M = s_off[g.NSB];
     // ---------------- PC: u = [W V]'v,  y = A22 v,  v'A22v ---------------------------------------------
     for (int q = blockIdx.x; q < 2 * c; q += G) {
       const double* col = (q < c) ? (W + (size_t)q * n) : (V + (size_t)(q - c) * n);
@@ -440,13 +510,13 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
       double vav = 0.0;
       if (threadIdx.x < NCONS) {
         if (g.S == 4)
-          symv_consumer<4>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+          symv_consumer<4>(a, g, M, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
         else if (g.S == 2)
-          symv_consumer<2>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+          symv_consumer<2>(a, g, M, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
         else
-          symv_consumer<1>(a, g, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
+          symv_consumer<1>(a, g, M, G, vcol, vav, ring, full, empty, st, vcs, stage, parity);
       } else if (threadIdx.x == NCONS) {
-        symv_producer(a, g, G, ring, full, empty, stage, parity);
+        symv_producer(a, g, M, G, ring, full, empty, stage, parity);
       }
       stage = __shfl_sync(0xffffffffu, stage, 0);  // producer warp: lanes follow lane 0
       parity = __shfl_sync(0xffffffffu, parity, 0);
@@ -480,7 +550,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
       // W[j+1, c] is needed by every thread for the next column: each CTA recomputes it with the
       // owner's exact procedure (same octet split, same order) so the value is bitwise identical.
       if (threadIdx.x < 8) {
-        const double wj1 = final_w(a, g, j + 1, threadIdx.x, c, V, W, vcol, s_u1, s_u2, tau, alpha);
+        const double wj1 = final_w(a, g, M, G, s_off, j + 1, threadIdx.x, c, V, W, vcol, s_u1, s_u2, tau, alpha);
         if (threadIdx.x == 0) {
           s_wrow[c] = wj1;
           s_vrow[c] = 1.0;
@@ -491,7 +561,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
       const int jn = j + 1;
       double ss = 0.0;
       for (int r = j + 1 + oct; r < n; r += nocts) {
-        const double w = final_w(a, g, r, sub, c, V, W, vcol, s_u1, s_u2, tau, alpha);
+        const double w = final_w(a, g, M, G, s_off, r, sub, c, V, W, vcol, s_u1, s_u2, tau, alpha);
         if (sub == 0) W[(size_t)c * n + r] = w;
         if (next) {
           double acc = (sub == 0) ? A[r + (long long)jn * lda] : 0.0;
@@ -525,6 +595,7 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
     return BK_OK;
   }
   BK_REQUIRE(nb >= 1 && nb <= NBMAX, "sytrd: panel width must be in 1..%d", NBMAX);
+  BK_REQUIRE(ceil_div(n, TR) <= SEGMAX, "sytrd: n too large (max %d)", SEGMAX * TR);
   int occ = 0;
   BK_REQUIRE(lda % 2 == 0, "sytrd: leading dimension must be even (16-byte aligned columns for TMA)");
   BK_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,7 +608,7 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
   BK_TRY(P.alloc((size_t)3 * nb * n));
   BK_TRY(part.alloc((size_t)2 * G));
   BK_TRY(dots.alloc((size_t)2 * nb));
-  BK_TRY(ypart.alloc((size_t)T * n));   // Tc <= T
+  BK_TRY(ypart.alloc((size_t)G * n));
   BK_TRY(ytpart.alloc((size_t)T * n));  // NSB <= T
   BK_TRY(ctx->barrier.ensure(4));
   DevBuf<long long> prof;
