@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(WM* WN * 32)
   }
   cp_async_wait<0>();
 
-  // epilogue
+  // epilogue: the accumulators go through shared memory (the pipeline buffers are free now) so that
+  // C is read and written with coalesced 16-byte row-contiguous accesses - the fragment layout itself
+  // would touch C in 64-byte pieces, one dependent load/store per accumulator.
+  __syncthreads();
   double* C = pr.C;
   long long ldc = pr.ldc;
   double alpha = pr.alpha, beta = pr.beta;
@@ -193,23 +196,44 @@ __global__ void __launch_bounds__(WM* WN * 32)
     alpha = 1.0;
     beta = 0.0;
   }
+  constexpr int CW = (BN < 64) ? BN : 64;  // columns staged per pass
+  constexpr int LDS = BM + 2;              // 2*LDS = 4 (mod 16): conflict-free fragment stores
+  static_assert((size_t)CW * LDS <= (size_t)STAGES * (A_STAGE + B_STAGE), "staging tile must fit");
+  double* Cs = smem;
+  const bool vecC = ((((uintptr_t)C) & 15u) == 0) && (ldc % 2 == 0);
 #pragma unroll
-  for (int i = 0; i < MT; ++i) {
-    const int row = m0 + wm0 + i * 8 + g;
-    if (row >= pr.m) continue;
+  for (int chunk = 0; chunk < BN / CW; ++chunk) {
+    const int c_lo = chunk * CW;
+    if (wn0 >= c_lo && wn0 < c_lo + CW) {
 #pragma unroll
-    for (int j = 0; j < NTL; ++j) {
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n0 + wn0 + j * 8 + 2 * t + e;
-        if (col < pr.n) {
-          double* c = C + row + (long long)col * ldc;
-          double v = alpha * acc[i][j][e];
-          if (beta != 0.0) v += beta * (*c);
-          *c = v;
+        for (int j = 0; j < NTL; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            Cs[(wn0 - c_lo + j * 8 + 2 * t + e) * LDS + wm0 + i * 8 + g] = acc[i][j][e];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (BM / 2) * CW; idx += NT) {
+      const int rp = idx % (BM / 2), cc = idx / (BM / 2);
+      const int row = m0 + 2 * rp, col = n0 + c_lo + cc;
+      if (row >= pr.m || col >= pr.n) continue;
+      const double v0 = alpha * Cs[cc * LDS + 2 * rp], v1 = alpha * Cs[cc * LDS + 2 * rp + 1];
+      double* cp = C + row + (long long)col * ldc;
+      if (vecC && row + 1 < pr.m) {
+        double2 o = make_double2(v0, v1);
+        if (beta != 0.0) {
+          const double2 old = *reinterpret_cast<const double2*>(cp);
+          o.x += beta * old.x;
+          o.y += beta * old.y;
         }
+        *reinterpret_cast<double2*>(cp) = o;
+      } else {
+        cp[0] = (beta != 0.0) ? v0 + beta * cp[0] : v0;
+        if (row + 1 < pr.m) cp[1] = (beta != 0.0) ? v1 + beta * cp[1] : v1;
       }
     }
+    if (chunk + 1 < BN / CW) __syncthreads();
   }
 }
 

@@ -9,6 +9,7 @@ namespace bk {
 struct SytrdStats {
   int launches = 0;
   double kernel_seconds = 0;     // sum of the panel-kernel durations (CUDA events)
+  double update_seconds = 0;     // sum of the rank-2nb trailing updates (DMMA GEMM)
   double algorithmic_bytes = 0;  // sum_j 4 (n-1-j)^2: the lower triangle read once per column
 };
 int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double* e, double* tau,

@@ -8,6 +8,7 @@
 // on the DMMA GEMM; T comes from S = V'V (split-K GEMM) and an ib-step triangular recurrence.
 // Only the k = lastkeeper columns that the fit will use are transformed: 4 n k ib flops per
 // block, 2 n^2 k in total.
+#include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
 #include "eigen.cuh"
@@ -57,7 +58,7 @@ __global__ void larft_kernel(const double* __restrict__ S, const double* __restr
 int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double* tau, double* Z,
                 long long ldz, int k) {
   if (n <= 1 || k <= 0) return BK_OK;
-  const int IB = 64;
+  const int IB = 128;  // wider blocks halve the passes over Z (the k = ib GEMMs are traffic bound)
   const int nref = n - 1;  // reflectors live in columns 0 .. n-2
   DevBuf<double> Vb, S, T, W1, W2;
   BK_TRY(Vb.alloc((size_t)n * IB));
@@ -65,6 +66,8 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
   BK_TRY(T.alloc((size_t)IB * IB));
   BK_TRY(W1.alloc((size_t)IB * k));
   BK_TRY(W2.alloc((size_t)IB * k));
+  BK_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * IB * IB)));
   const int nblocks = (int)ceil_div(nref, IB);
   for (int b = nblocks - 1; b >= 0; --b) {
     const int j0 = b * IB;
@@ -75,7 +78,7 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
                       ctx->stream>>>(A, lda, j0, ib, mrows, Vb.p);
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, true, false, ib, ib, mrows, 1.0, Vb.p, mrows, Vb.p, mrows, 0.0, S.p, ib));
-    larft_kernel<<<1, 64, sizeof(double) * ib * ib, ctx->stream>>>(S.p, tau + j0, ib, T.p);
+    larft_kernel<<<1, IB, sizeof(double) * ib * ib, ctx->stream>>>(S.p, tau + j0, ib, T.p);
     BK_LAUNCHED(ctx);
     BK_CUDA(cudaGetLastError());
     double* Zb = Z + (j0 + 1);
@@ -106,6 +109,9 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
   SytrdStats sst;
   BK_TRY(sytrd_lower(ctx, work, ldw, n, d.p, e.p, tau.p, 64, &sst));
   const double t_tri = tm.stop();
+  if (getenv("BK_EIG_VERBOSE"))
+    fprintf(stderr, "[eigen n=%d] tridiag %.4f s: panel kernels %.4f, trailing GEMMs %.4f, other %.4f\n", n, t_tri,
+            sst.kernel_seconds, sst.update_seconds, t_tri - sst.kernel_seconds - sst.update_seconds);
   std::vector<double> dh(n), eh(n), ev(n);
   BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -451,11 +451,12 @@ __global__ void __launch_bounds__(256)
     dc_u_kernel(const MergeDesc* __restrict__ descs, const double* __restrict__ dlam,
                 const int* __restrict__ org, const double* __restrict__ mu,
                 const double* __restrict__ zhat, const int* __restrict__ grow,
-                double* __restrict__ U, long long ldu) {
+                double* __restrict__ U, long long ldu, const int* __restrict__ colmap) {
   __shared__ double red[32];
   const MergeDesc m = descs[blockIdx.y];
   const int K = m.K;
-  const int j = blockIdx.x;
+  // colmap (root merge with truncation): only the wanted roots are formed, packed left
+  const int j = colmap ? colmap[blockIdx.x] : (int)blockIdx.x;
   if (j >= K) return;
   const double* dl = dlam + m.lo;
   const int* og = org + m.lo;
@@ -469,10 +470,22 @@ __global__ void __launch_bounds__(256)
   }
   s = block_sum(s, red);
   const double inv = 1.0 / sqrt(s);
-  double* ucol = U + m.lo + (long long)(m.lo + j) * ldu;
+  double* ucol = U + m.lo + (long long)(m.lo + (int)blockIdx.x) * ldu;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const double u = zh[i] / ((dl[i] - dorg) - muj);
     ucol[grow[m.lo + i]] = u * inv;
+  }
+}
+
+// ---- dst[:, dstcol[i]] = src[:, srccol[i]] --------------------------------------------------------------
+__global__ void dc_assemble_kernel(const double* __restrict__ src, long long lds, const int* __restrict__ srccol,
+                                   double* __restrict__ dst, long long ldd, const int* __restrict__ dstcol,
+                                   int rows, int count) {
+  const long long total = (long long)rows * count;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % rows), i = (int)(idx / rows);
+    dst[r + (long long)dstcol[i] * ldd] = src[r + (long long)srccol[i] * lds];
   }
 }
 
@@ -532,6 +545,26 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
   }
   std::vector<double> Dh(n), zh(n);
   if (stats) *stats = StedcStats();
+  std::vector<int> order(n);
+  int want = 0;
+  bool root_done = false;
+  // ascending eigenvalues + the reference's truncation rule on the leading max_want values
+  // (R/bigKRLS_Rcpp_functions.R:190: lastkeeper = max(which(values >= eigtrunc*values[1])))
+  auto finalize_values = [&](const std::vector<double>& D) -> int {
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return D[a] < D[b]; });
+    for (int i = 0; i < n; ++i) {
+      if (!std::isfinite(D[order[i]])) {
+        set_error("stedc: non-finite eigenvalue");
+        return BK_ERR_NUMERIC;
+      }
+      evals_host[i] = D[order[i]];
+    }
+    want = 0;
+    for (int c = 0; c < max_want; ++c)
+      if (evals_host[n - 1 - c] >= rel_thresh * evals_host[n - 1]) want = c + 1;
+    return BK_OK;
+  };
 
   for (int h = 1; h <= height; ++h) {
     std::vector<Node> lvl;
@@ -675,11 +708,70 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
       dc_secular_kernel<<<dim3((unsigned)ceil_div(maxK, 128), nm), 128, 0, ctx->stream>>>(
           desc_d.p, dlam_d.p, w_d.p, org_d.p, mu_d.p, Dnew.p, fail_d.p);
       BK_LAUNCHED(ctx);
+      if (h == height && nm == 1) {
+        // Root merge: all eigenvalues are known now.  When only part of the eigenvectors is wanted
+        // (eigtrunc / Neig, or values only) form just those columns of U: the root GEMM shrinks from
+        // n x K x K to n x K x (wanted roots).
+        BK_CUDA(cudaMemcpyAsync(Dh.data(), Dnew.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));
+        BK_TRY(finalize_values(Dh));
+        if (!Z || want < n) {
+          const MergeDesc& md = descs[0];
+          const int K = md.K;
+          std::vector<int> colmap, rsrc, rdst, dsrc, ddst;
+          for (int c = 0; Z && c < want; ++c) {
+            const int pos = order[n - 1 - c];  // position in D: [0,K) roots, [K,n) deflated (columns of G)
+            if (pos < K) {
+              rsrc.push_back((int)colmap.size());
+              colmap.push_back(pos);
+              rdst.push_back(c);
+            } else {
+              dsrc.push_back(pos);
+              ddst.push_back(c);
+            }
+          }
+          const int nwr = (int)colmap.size();
+          DevBuf<int> colmap_d, rsrc_d, rdst_d, dsrc_d, ddst_d;
+          if (nwr > 0) {
+            BK_TRY(upload(ctx, colmap_d, colmap));
+            BK_TRY(upload(ctx, rsrc_d, rsrc));
+            BK_TRY(upload(ctx, rdst_d, rdst));
+            dc_zhat_kernel<<<dim3((unsigned)ceil_div(maxK, 128), nm), 128, 0, ctx->stream>>>(
+                desc_d.p, dlam_d.p, w_d.p, org_d.p, mu_d.p, zhat_d.p);
+            BK_LAUNCHED(ctx);
+            dc_u_kernel<<<dim3((unsigned)nwr, 1), 256, 0, ctx->stream>>>(desc_d.p, dlam_d.p, org_d.p, mu_d.p,
+                                                                         zhat_d.p, grow_d.p, U.p, ld, colmap_d.p);
+            BK_LAUNCHED(ctx);
+            for (auto& pr : probs) pr.n = nwr;
+            BK_TRY(upload(ctx, probs_d, probs));
+            BK_TRY(gemm_batched(ctx, false, false, probs_d.p, (int)probs.size(), gm_max_m, nwr, vec));
+            if (stats)
+              stats->merge_flops -= 2LL * (K - nwr) * ((long long)(md.mid - md.lo) * (md.c1 + md.c2) +
+                                                     (long long)(md.hi - md.mid) * (md.c2 + md.c3));
+            dc_assemble_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * nwr, 256), 8LL * ctx->sm_count),
+                                 256, 0, ctx->stream>>>(Q.p, ld, rsrc_d.p, Z, ldz, rdst_d.p, n, nwr);
+            BK_LAUNCHED(ctx);
+          }
+          if (!dsrc.empty()) {
+            BK_TRY(upload(ctx, dsrc_d, dsrc));
+            BK_TRY(upload(ctx, ddst_d, ddst));
+            dc_assemble_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * (long long)dsrc.size(), 256),
+                                                               8LL * ctx->sm_count),
+                                 256, 0, ctx->stream>>>(Gm.p, ld, dsrc_d.p, Z, ldz, ddst_d.p, n, (int)dsrc.size());
+            BK_LAUNCHED(ctx);
+          }
+          BK_CUDA(cudaGetLastError());
+          BK_CUDA(cudaStreamSynchronize(ctx->stream));
+          if (stats) stats->levels = h;
+          root_done = true;
+          break;
+        }
+      }
       dc_zhat_kernel<<<dim3((unsigned)ceil_div(maxK, 128), nm), 128, 0, ctx->stream>>>(
           desc_d.p, dlam_d.p, w_d.p, org_d.p, mu_d.p, zhat_d.p);
       BK_LAUNCHED(ctx);
       dc_u_kernel<<<dim3((unsigned)maxK, nm), 256, 0, ctx->stream>>>(desc_d.p, dlam_d.p, org_d.p, mu_d.p,
-                                                                     zhat_d.p, grow_d.p, U.p, ld);
+                                                                     zhat_d.p, grow_d.p, U.p, ld, nullptr);
       BK_LAUNCHED(ctx);
       BK_TRY(upload(ctx, probs_d, probs));
       BK_TRY(gemm_batched(ctx, false, false, probs_d.p, (int)probs.size(), gm_max_m, gm_max_n, vec));
@@ -700,37 +792,26 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
 
   // final ordering
   int fail = 0;
-  BK_CUDA(cudaMemcpyAsync(Dh.data(), Dcur.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaMemcpyAsync(&fail, fail_d.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!root_done)
+    BK_CUDA(cudaMemcpyAsync(Dh.data(), Dcur.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (fail) {
     set_error("stedc: %s did not converge", fail == 1 ? "leaf QL iteration" : "secular equation");
     return BK_ERR_NUMERIC;
   }
-  std::vector<int> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Dh[a] < Dh[b]; });
-  for (int i = 0; i < n; ++i) {
-    if (!std::isfinite(Dh[order[i]])) {
-      set_error("stedc: non-finite eigenvalue");
-      return BK_ERR_NUMERIC;
+  if (!root_done) {
+    BK_TRY(finalize_values(Dh));
+    if (want > 0 && Z) {
+      std::vector<int> perm(want);
+      for (int c = 0; c < want; ++c) perm[c] = order[n - 1 - c];  // descending
+      DevBuf<int> perm_d;
+      BK_TRY(upload(ctx, perm_d, perm));
+      BK_TRY(gather_columns(ctx, Q.p, ld, n, want, perm_d.p, Z, ldz));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    evals_host[i] = Dh[order[i]];
   }
-  // eigenvectors wanted: the largest max_want, cut at evals >= rel_thresh * largest
-  // (R/bigKRLS_Rcpp_functions.R:190: lastkeeper = max(which(values >= eigtrunc*values[1])))
-  int want = 0;
-  for (int c = 0; c < max_want; ++c)
-    if (evals_host[n - 1 - c] >= rel_thresh * evals_host[n - 1]) want = c + 1;
   if (n_want) *n_want = want;
-  if (want > 0 && Z) {
-    std::vector<int> perm(want);
-    for (int c = 0; c < want; ++c) perm[c] = order[n - 1 - c];  // descending
-    DevBuf<int> perm_d;
-    BK_TRY(upload(ctx, perm_d, perm));
-    BK_TRY(gather_columns(ctx, Q.p, ld, n, want, perm_d.p, Z, ldz));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
   return BK_OK;
 }
 

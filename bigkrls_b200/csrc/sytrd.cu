@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
     __syncthreads();
     const long long M = s_off[g.NSB];
     // ---------------- PC: u = [W V]'v,  y = A22 v,  v'A22v ---------------------------------------------
+    const long long tpc0 = clock64();
     for (int q = blockIdx.x; q < 2 * c; q += G) {
       const double* col = (q < c) ? (W + (size_t)q * n) : (V + (size_t)(q - c) * n);
       double s = 0.0;
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
       vav = block_sum(vav, red);
       if (threadIdx.x == 0) a.part[G + blockIdx.x] = vav;
     }
+    if (a.prof && threadIdx.x == 0) a.prof[16 + blockIdx.x] += clock64() - tpc0;
     PROF(3);
     grid_barrier(a.barrier, epoch);
     PROF(4);
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
         s_scal[0] = -0.5 * tau * (tau * (vav - 2.0 * uu));
       }
       __syncthreads();
+      PROF(5);
       const double alpha = s_scal[0];
       // W[j+1, c] is needed by every thread for the next column: each CTA recomputes it with the
       // owner's exact procedure (same octet split, same order) so the value is bitwise identical.
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
         }
       }
       __syncthreads();
+      PROF(7);
       const bool next = (c + 1 < nb);  // the next panel's prologue handles its own first column
       const int jn = j + 1;
       double ss = 0.0;
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(NTH, 1) sytrd_panel_kernel(SytrdArgs a) {
           }
         }
       }
-      PROF(5);
+      PROF(8);
       if (next) {
         ss = block_sum(ss, red);
         if (threadIdx.x == 0) a.part[blockIdx.x] = ss;
@@ -614,16 +618,17 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
   DevBuf<long long> prof;
   const bool do_prof = getenv("BK_SYTRD_PROF") != nullptr;
   if (do_prof) {
-    BK_TRY(prof.alloc(8));
-    BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+    BK_TRY(prof.alloc(16 + 2 * G));
+    BK_CUDA(cudaMemsetAsync(prof.p, 0, (16 + 2 * G) * sizeof(long long), ctx->stream));
   }
 
   // per-panel CUDA events on the launching stream: the roofline numbers of bench.py are the
   // sum of these kernel durations against the algorithmic bytes 4 m_j^2 per column
   const int npanels = (int)ceil_div(n, nb);
-  std::vector<cudaEvent_t> ev0(stats ? npanels : 0), ev1(stats ? npanels : 0);
+  std::vector<cudaEvent_t> ev0(stats ? npanels : 0), ev1(stats ? npanels : 0), ev2(stats ? npanels : 0);
   for (auto& x : ev0) BK_CUDA(cudaEventCreate(&x));
   for (auto& x : ev1) BK_CUDA(cudaEventCreate(&x));
+  for (auto& x : ev2) BK_CUDA(cudaEventCreate(&x));
   int pi = 0;
   for (int j0 = 0; j0 < n; j0 += nb, ++pi) {
     BK_CUDA(cudaMemsetAsync(P.p, 0, sizeof(double) * (size_t)3 * nb * n, ctx->stream));
@@ -657,28 +662,41 @@ int sytrd_lower(bk_ctx* ctx, double* A, long long lda, int n, double* d, double*
       BK_TRY(gemm(ctx, false, true, m, m, 2 * nb, -1.0, P.p + jn, n, P.p + (size_t)nb * n + jn, n,
                   1.0, A + jn + (long long)jn * lda, lda, true));
     }
+    if (stats) BK_CUDA(cudaEventRecord(ev2[pi], ctx->stream));
   }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));  // workspaces are freed on return
   if (do_prof) {
-    long long h[8];
-    BK_CUDA(cudaMemcpy(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost));
-    const char* names[7] = {"PB", "wait(B2)", "PC dots", "PC symv", "wait(B3)", "PD", "wait(B1)"};
+    std::vector<long long> h(16 + 2 * G);
+    BK_CUDA(cudaMemcpy(h.data(), prof.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const char* names[9] = {"PB", "wait(B2)", "PC dots", "PC symv", "wait(B3)", "PD setup", "wait(B1)", "PD wj1", "PD rows"};
     long long tot = 0;
-    for (int i = 0; i < 7; ++i) tot += h[i];
+    for (int i = 0; i < 9; ++i) tot += h[i];
     fprintf(stderr, "[sytrd prof n=%d] CTA0 cycles:", n);
-    for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (double)tot);
+    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (double)tot);
     fprintf(stderr, " total=%.3f Gcyc\n", tot * 1e-9);
+    long long mn = 1LL << 62, mx = 0, sm = 0;
+    for (int b = 0; b < G; ++b) {
+      mn = std::min(mn, h[16 + b]);
+      mx = std::max(mx, h[16 + b]);
+      sm += h[16 + b];
+    }
+    fprintf(stderr, "[sytrd prof] per-CTA PC (dots+symv) cycles: min %.3f mean %.3f max %.3f Gcyc\n", mn * 1e-9,
+            sm * 1e-9 / G, mx * 1e-9);
   }
   if (stats) {
     stats->launches = npanels;
     stats->kernel_seconds = 0.0;
+    stats->update_seconds = 0.0;
     stats->algorithmic_bytes = 0.0;
     for (int i = 0; i < npanels; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev0[i], ev1[i]);
       stats->kernel_seconds += 1e-3 * ms;
+      cudaEventElapsedTime(&ms, ev1[i], ev2[i]);
+      stats->update_seconds += 1e-3 * ms;
       cudaEventDestroy(ev0[i]);
       cudaEventDestroy(ev1[i]);
+      cudaEventDestroy(ev2[i]);
     }
     for (int j = 0; j < n - 1; ++j) {
       const double m = (double)(n - 1 - j);
