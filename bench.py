@@ -50,50 +50,55 @@ def synthetic(N, P, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML
+    (pynvml) from a background thread once per second; `nvidia-smi -lms 200` from a subprocess measurably
+    slowed the timed region (it perturbs the launch-bound parts of the fit)."""
 
-    def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+    def __init__(self, device, period=1.0):
+        self.device, self.period, self.rows = device, period, []
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self.thread = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                              ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.thread.join(timeout=3)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({k for _, rs in self.rows for k, bit in names.items() if rs & bit})
         busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": float(self.mx),
+                "reasons": reasons, "samples": len(sm), "source": "nvml, 1 Hz"}
 
 
 def measured_peaks():
@@ -245,6 +250,14 @@ def main():
     info = infos[-1]
     peak, peak_src = measured_peaks()
     ach = info["sytrd_bytes"] / info["sytrd_kernel_seconds"] * 1e-9 if info["sytrd_kernel_seconds"] > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_sytrd_traffic.json")))
+        traffic = tr["traffic_over_algorithmic"] * info["sytrd_bytes"] / max(1.0, info["sytrd_launches"])
+        traffic_src = ("dram__bytes_read+write of one ncu --set full capture (launch 40, ratio %.3f to its algorithmic "
+                       "bytes) scaled to the average launch" % tr["traffic_over_algorithmic"])
+    except Exception:  # noqa: BLE001
+        pass
     stage = {k: float(np.mean([i[k] for i in infos])) for k in
              ("t_kernel", "t_eigen", "t_tridiag", "t_dc", "t_backtransform", "t_lambda", "t_coef", "t_vcov",
               "t_deriv", "t_total")}
@@ -263,7 +276,7 @@ def main():
                          "launches_per_step": int(info["sytrd_launches"]),
                          "algorithmic_bytes_per_launch": info["sytrd_bytes"] / max(1.0, info["sytrd_launches"]),
                          "avg_launch_seconds": info["sytrd_kernel_seconds"] / max(1.0, info["sytrd_launches"]),
-                         "traffic": None},
+                         "traffic": traffic, "traffic_source": traffic_src},
             "stage_seconds": stage,
             "fit": {"lambda": info["lambda"], "lastkeeper": int(info["lastkeeper"]), "n_probes": info["n_probes"],
                     "n_passes": info["n_passes"], "dc_top_k": int(info["dc_top_k"])}}
