@@ -59,7 +59,8 @@ class FitInfo(C.Structure):
                 ("sytrd_launches", C.c_double), ("sytrd_kernel_seconds", C.c_double),
                 ("sytrd_bytes", C.c_double),
                 ("dc_levels", C.c_double), ("dc_merge_flops", C.c_double), ("dc_top_n", C.c_double),
-                ("dc_top_k", C.c_double), ("gpu_launches", C.c_double)]
+                ("dc_top_k", C.c_double), ("gpu_launches", C.c_double),
+                ("krylov_matvecs", C.c_double), ("krylov_restarts", C.c_double)]
 
     def as_dict(self):
         d = {}

@@ -67,6 +67,14 @@ int bk_eigen(bk_ctx* ctx, const double* A, int64_t n, int64_t neig, double* vals
   DevBuf<double> dA, Z;
   BK_TRY(h2d(ctx, dA, A, (size_t)n * n));
   if (vecs) BK_TRY(Z.alloc((size_t)n * neig));
+  if (use_topk(n, neig)) {
+    // Neig << N: block-Krylov path (reference: sp_mat + eigs_sym, src/eigen.cpp:18-22)
+    std::vector<double> evk(neig);
+    BK_TRY(eigen_topk(ctx, dA.p, n, (int)n, (int)neig, evk.data(), vecs ? Z.p : nullptr, n, nullptr));
+    for (int64_t i = 0; i < neig; ++i) vals[i] = evk[i];
+    if (vecs) return d2h(ctx, vecs, Z.p, (size_t)n * neig);
+    return BK_OK;
+  }
   std::vector<double> ev(n);
   int nw = 0;
   // rel_thresh = -inf: keep all neig leading vectors (truncation is the caller's business,

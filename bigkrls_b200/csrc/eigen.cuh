@@ -47,6 +47,17 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
                double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times);
 inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
 
+// Top-k eigenpairs (k << n) by restarted block Krylov + Rayleigh-Ritz (eigen_topk.cu): evals_host[k]
+// DESCENDING, Z (n x k) eigenvectors.  K is only read.
+struct TopkStats {
+  int restarts = 0, matvecs = 0, block = 0, basis = 0;
+  double residual = 0;
+};
+int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
+               long long ldz, TopkStats* stats);
+// policy shared by bk_eigen and the fused fit
+inline bool use_topk(long long n, long long neig) { return n >= 512 && neig * 3 <= n; }
+
 // Pure host logic of one D&C merge, exported for the CPU unit tests (tests/test_host_logic.py)
 struct MergePlan {
   int K = 0;

@@ -1,0 +1,224 @@
+// Top-k eigenpairs of a symmetric (PSD kernel) matrix by a restarted block-Krylov method with full
+// re-orthogonalisation and Rayleigh-Ritz.  Replaces the `Neig < N` branch of the reference,
+// `sp_mat(A)` + `arma::eigs_sym(vals, vecs, sparseA, Neig)` (src/eigen.cpp:18-22; ARPACK/NEWARP implicitly
+// restarted Lanczos to machine tolerance) - the dense-to-sparse copy is gone, the dense K is used as is.
+// Executable specification: tests/krylov_prototype.py.
+//
+//   expand   W = K X                          DMMA GEMM  n x n x b      (HBM: one read of K per block)
+//            W -= V (V'W)  (twice), X = orth(W)                        (Gram matrix + small eigensolve)
+//   extract  H = V'(KV),  (theta, S) = eig(H) (our own dense eigensolver on the m x m matrix)
+//            Q = V S, KQ = KV S, residuals ||KQ - Q theta||
+//   restart  V <- Q (thick restart), next block = orthonormalised worst residuals
+//
+// All O(n m b) work is on the GEMM; the host only sees m-vectors (Ritz values, residual norms).
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "eigen.cuh"
+#include "kernels.cuh"
+
+namespace bk {
+
+__global__ void hash_fill_kernel(double* p, long long n, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long x = (unsigned long long)i * 6364136223846793005ULL + seed;
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    p[i] = (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
+
+// R[:, j] = KQ[:, j] - theta[j] * Q[:, j];  nrm2[j] = ||R[:, j]||^2   (one CTA per column)
+__global__ void ritz_residual_kernel(const double* __restrict__ Q, const double* __restrict__ KQ,
+                                     const double* __restrict__ theta, int n, double* __restrict__ R,
+                                     double* __restrict__ nrm2) {
+  __shared__ double red[32];
+  const int j = blockIdx.x;
+  const double th = theta[j];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double r = KQ[i + (long long)j * n] - th * Q[i + (long long)j * n];
+    R[i + (long long)j * n] = r;
+    s = fma(r, r, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) nrm2[j] = s;
+}
+
+namespace {
+
+struct Ws {
+  bk_ctx* ctx;
+  int n;
+  DevBuf<double> G, Gs, T1, T2, scale;
+};
+
+// X (n x b, ld n) <- orthonormal basis of its span via the eigen-decomposition of the Gram matrix,
+// applied twice.  Returns the number of columns kept (directions with relative Gram eigenvalue below
+// `drop` are discarded - Krylov breakdown / rank deficiency).
+int orth_gram(Ws& w, double* X, int b, int* kept) {
+  bk_ctx* ctx = w.ctx;
+  const int n = w.n;
+  int r = b;
+  for (int pass = 0; pass < 2 && r > 0; ++pass) {
+    BK_TRY(w.G.ensure((size_t)r * r));
+    BK_TRY(w.Gs.ensure((size_t)r * r));
+    BK_TRY(w.T1.ensure((size_t)n * r));
+    BK_TRY(w.scale.ensure(r));
+    BK_TRY(gemm(ctx, true, false, r, r, n, 1.0, X, n, X, n, 0.0, w.G.p, r));
+    std::vector<double> ev(r);
+    int nw = 0;
+    BK_TRY(eigen_full(ctx, w.G.p, r, r, ev.data(), r, -INFINITY, &nw, w.Gs.p, r, nullptr));
+    int keep = 0;
+    std::vector<double> sc(r, 0.0);
+    for (int j = 0; j < r; ++j)
+      if (ev[j] > 1e-14 * ev[0] && ev[j] > 0.0) {
+        sc[j] = 1.0 / std::sqrt(ev[j]);
+        keep = j + 1;
+      } else {
+        break;
+      }
+    if (keep == 0) {
+      r = 0;
+      break;
+    }
+    BK_CUDA(cudaMemcpyAsync(w.scale.p, sc.data(), sizeof(double) * keep, cudaMemcpyHostToDevice, ctx->stream));
+    BK_TRY(col_scale(ctx, w.Gs.p, r, r, keep, w.scale.p, nullptr, w.Gs.p, r));
+    BK_TRY(gemm(ctx, false, false, n, keep, r, 1.0, X, n, w.Gs.p, r, 0.0, w.T1.p, n));
+    BK_TRY(copy_matrix(ctx, w.T1.p, n, n, keep, 1.0, X, n));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));  // sc / ev are host temporaries
+    r = keep;
+  }
+  *kept = r;
+  return BK_OK;
+}
+
+// W (n x b) -= V (V' W), twice (classical Gram-Schmidt with re-orthogonalisation)
+int project_out(Ws& w, const double* V, int m, double* W, int b) {
+  if (m <= 0 || b <= 0) return BK_OK;
+  BK_TRY(w.T2.ensure((size_t)m * b));
+  for (int pass = 0; pass < 2; ++pass) {
+    BK_TRY(gemm(w.ctx, true, false, m, b, w.n, 1.0, V, w.n, W, w.n, 0.0, w.T2.p, m));
+    BK_TRY(gemm(w.ctx, false, false, w.n, b, m, -1.0, V, w.n, w.T2.p, m, 1.0, W, w.n));
+  }
+  return BK_OK;
+}
+
+}  // namespace
+
+int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
+               long long ldz, TopkStats* stats) {
+  BK_REQUIRE(k >= 1 && k <= n, "eigen_topk: k must be in 1..n");
+  const int b = std::min(128, std::max(8, std::min(n, (k + 3) / 4)));
+  const int m_max = std::min(n, k + 8 * b);
+  const double tol = 2e-13;
+  Ws w;
+  w.ctx = ctx;
+  w.n = n;
+  DevBuf<double> V, KV, Wt, Qb, KQb, H, S, theta_d, nrm_d, Rb;
+  DevBuf<int> idx_d;
+  BK_TRY(V.alloc((size_t)n * (m_max + b)));
+  BK_TRY(KV.alloc((size_t)n * (m_max + b)));
+  BK_TRY(Wt.alloc((size_t)n * b));
+  BK_TRY(Qb.alloc((size_t)n * k));
+  BK_TRY(KQb.alloc((size_t)n * k));
+  BK_TRY(Rb.alloc((size_t)n * k));
+  BK_TRY(H.alloc((size_t)m_max * m_max));
+  BK_TRY(S.alloc((size_t)m_max * k));
+  BK_TRY(theta_d.alloc(k));
+  BK_TRY(nrm_d.alloc(k));
+  BK_TRY(idx_d.alloc(b));
+
+  // deterministic pseudo-random start block
+  hash_fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(V.p, (long long)n * b, 0x9E3779B97F4A7C15ULL);
+  BK_LAUNCHED(ctx);
+  int bx = 0;
+  BK_TRY(orth_gram(w, V.p, b, &bx));
+  int m = 0;  // accepted basis columns; the candidate block X sits at V[:, m : m+bx]
+  std::vector<double> th(k), nrm(k);
+  int outer = 0, matvecs = 0;
+  const int max_outer = 300;
+  for (; outer < max_outer; ++outer) {
+    // ---- expand the Krylov basis ------------------------------------------------------------------
+    while (bx > 0 && m + bx <= m_max) {
+      double* X = V.p + (size_t)m * n;
+      double* KX = KV.p + (size_t)m * n;
+      BK_TRY(gemm(ctx, false, false, n, bx, n, 1.0, K, ldk, X, n, 0.0, KX, n));
+      matvecs += bx;
+      m += bx;
+      BK_TRY(copy_matrix(ctx, KX, n, n, bx, 1.0, Wt.p, n));
+      BK_TRY(project_out(w, V.p, m, Wt.p, bx));
+      int r = 0;
+      BK_TRY(orth_gram(w, Wt.p, bx, &r));
+      bx = r;
+      if (bx > 0 && m + bx <= m_max + b) BK_TRY(copy_matrix(ctx, Wt.p, n, n, bx, 1.0, V.p + (size_t)m * n, n));
+      if (m + bx > m_max) break;
+    }
+    if (m < k) {
+      // the Krylov space is exhausted (exact invariant subspace smaller than k): restart direction
+      set_error("eigen_topk: Krylov breakdown with %d < %d basis vectors", m, k);
+      return BK_ERR_NUMERIC;
+    }
+    // ---- Rayleigh-Ritz -----------------------------------------------------------------------------
+    BK_TRY(gemm(ctx, true, false, m, m, n, 1.0, V.p, n, KV.p, n, 0.0, H.p, m));
+    std::vector<double> ev(m);
+    int nw = 0;
+    BK_TRY(eigen_full(ctx, H.p, m, m, ev.data(), k, -INFINITY, &nw, S.p, m, nullptr));
+    for (int j = 0; j < k; ++j) th[j] = ev[j];
+    BK_CUDA(cudaMemcpyAsync(theta_d.p, th.data(), sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+    BK_TRY(gemm(ctx, false, false, n, k, m, 1.0, V.p, n, S.p, m, 0.0, Qb.p, n));
+    BK_TRY(gemm(ctx, false, false, n, k, m, 1.0, KV.p, n, S.p, m, 0.0, KQb.p, n));
+    ritz_residual_kernel<<<k, 256, 0, ctx->stream>>>(Qb.p, KQb.p, theta_d.p, n, Rb.p, nrm_d.p);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(cudaMemcpyAsync(nrm.data(), nrm_d.p, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    double worst = 0.0;
+    for (int j = 0; j < k; ++j) worst = std::max(worst, std::sqrt(nrm[j]));
+    if (!(worst == worst)) {
+      set_error("eigen_topk: non-finite residual (NaN/Inf in the input?)");
+      return BK_ERR_NUMERIC;
+    }
+    if (worst <= tol * std::fabs(th[0]) || m >= n) break;
+    // ---- thick restart with the Ritz vectors; next block = worst residual directions ---------------
+    std::vector<int> order(k);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return nrm[a] > nrm[c]; });
+    const int nb = std::min(b, k);
+    BK_CUDA(cudaMemcpyAsync(idx_d.p, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    BK_TRY(gather_columns(ctx, Rb.p, n, n, nb, idx_d.p, Wt.p, n));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, V.p, n));
+    BK_TRY(copy_matrix(ctx, KQb.p, n, n, k, 1.0, KV.p, n));
+    m = k;
+    BK_TRY(project_out(w, V.p, m, Wt.p, nb));
+    BK_TRY(orth_gram(w, Wt.p, nb, &bx));
+    if (bx > 0) BK_TRY(copy_matrix(ctx, Wt.p, n, n, bx, 1.0, V.p + (size_t)m * n, n));
+    if (bx == 0) break;  // residuals vanish numerically: converged as far as FP64 goes
+  }
+  double worst = 0.0;
+  for (int j = 0; j < k; ++j) worst = std::max(worst, std::sqrt(nrm[j]));
+  if (worst > 1e-9 * std::fabs(th[0])) {
+    set_error("eigen_topk: no convergence after %d restarts (residual %.3e relative)", outer,
+              worst / std::fabs(th[0]));
+    return BK_ERR_NUMERIC;
+  }
+  for (int j = 0; j < k; ++j) evals_host[j] = th[j];
+  if (Z) BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, Z, ldz));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    stats->restarts = outer + 1;
+    stats->matvecs = matvecs;
+    stats->block = b;
+    stats->basis = m_max;
+    stats->residual = worst / std::fabs(th[0]);
+  }
+  return BK_OK;
+}
+
+}  // namespace bk

@@ -251,7 +251,18 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     if (!multi || comm->rank == 0) {
       std::vector<double> ev(n);
       EigenTimes et;
-      BK_TRY(eigen_full(ctx, f->K.p, ld, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et));
+      if (use_topk(n, f->neig)) {
+        // Neig << N (reference: sp_mat + eigs_sym, src/eigen.cpp:18-22): restarted block Krylov
+        TopkStats ts;
+        BK_TRY(eigen_topk(ctx, f->K.p, ld, n, f->neig, ev.data(), Zfull.p, ld, &ts));
+        k = 0;  // lastkeeper over the Neig values (R/bigKRLS_Rcpp_functions.R:190)
+        for (int i = 0; i < f->neig; ++i)
+          if (ev[i] >= o.eigtrunc * ev[0]) k = i + 1;
+        f->info.krylov_matvecs = ts.matvecs;
+        f->info.krylov_restarts = ts.restarts;
+      } else {
+        BK_TRY(eigen_full(ctx, f->K.p, ld, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et));
+      }
       for (int i = 0; i < f->neig; ++i) f->evals[i] = ev[i];
       f->info.t_tridiag = et.tridiag;
       f->info.t_dc = et.dc;

@@ -175,6 +175,8 @@ typedef struct bk_fit_info {
   double dc_levels, dc_merge_flops, dc_top_n, dc_top_k;
   /* kernels launched by the library during this fit */
   double gpu_launches;
+  /* Neig << N path (block Krylov): matrix-vector products with K and thick restarts (0 on the full path) */
+  double krylov_matvecs, krylov_restarts;
 } bk_fit_info;
 
 /* Xs (n x p) and ys (n) are the STANDARDISED data (R/bigKRLS.R:251-254), host pointers.

@@ -58,6 +58,7 @@ def test_mtcars_reference_known_answers():
     (900, 8, 4, dict(eigtrunc=0.01, which_derivatives=[1, 3, 5])),
     (600, 5, 5, dict(lambda_=0.5)),
     (3100, 5, 6, dict()),                       # n > 3000 -> default eigtrunc = 0.001
+    (2400, 8, 7, dict(Neig=300, eigtrunc=0.001, which_derivatives=[1, 3, 5])),   # config-4 shape: Krylov path
 ])
 def test_fit_parity_synthetic(n, p, seed, kw):
     kw = dict(kw)

@@ -182,6 +182,18 @@ def test_eigen_top_neig_and_values_only(ctx):
     assert np.array_equal(vals2[:neig], vals)
 
 
+@pytest.mark.parametrize("n,neig,p", [(1500, 120, 5), (2048, 64, 10), (3000, 500, 20)])
+def test_eigen_topk_krylov(ctx, n, neig, p):
+    # Neig << N -> restarted block-Krylov path (reference: sp_mat + eigs_sym, src/eigen.cpp:18-22)
+    lib = _lib.load()
+    X, y = o.synthetic(n, p, 1004)
+    Xs, *_ = o.standardize(X, y)
+    A = o.gauss_kernel(Xs, p)
+    vals, vecs = np.empty(neig), np.empty((n, neig), order="F")
+    check(lib.bk_eigen(ctx.handle, dptr(A), n, neig, dptr(vals), dptr(vecs)))
+    _check_eig(A, vals, vecs)
+
+
 @pytest.mark.parametrize("binary", [False, True])
 def test_deriv_mat(ctx, binary):
     lib = _lib.load()

@@ -16,6 +16,10 @@ kw = {}
 if len(sys.argv) > 3:
     kw["eigtrunc"] = float(sys.argv[3])
 reps = 1 if (len(sys.argv) > 4 and sys.argv[4] == "once") else 2
+if len(sys.argv) > 5:
+    kw["Neig"] = int(sys.argv[5])
+if len(sys.argv) > 6:
+    kw["which_derivatives"] = [int(v) for v in sys.argv[6].split(",")]
 X, y = o.synthetic(N, P, 1003 if (N, P) == (20000, 10) else 1000 + P)
 for rep in range(reps):
     t0 = time.time()
