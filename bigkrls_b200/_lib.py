@@ -118,10 +118,12 @@ _SIGNATURES = {
     "bk_fit_predict": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p]),
     "bk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_double_p]),
     "bk_dgemm_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
-                                 C.c_int, c_double_p]),
+                                 C.c_double, C.c_int, c_double_p]),
     "bk_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p,
                                 C.c_int64, c_double_p, C.c_int64, C.c_double, c_double_p, C.c_int64, C.c_int, C.c_int]),
     "bk_debug_sytrd": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "bk_debug_twostage": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p,
+                                    c_double_p, C.c_int64, c_double_p]),
     "bk_debug_stedc": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
     "bk_host_lambda_search": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                         C.c_int, C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p,

@@ -240,6 +240,45 @@ int bk_debug_sytrd(bk_ctx* ctx, const double* A, int64_t n, double* d, double* e
   return BK_OK;
 }
 
+int bk_debug_twostage(bk_ctx* ctx, const double* A, int64_t n, double* band, double* d, double* e, double* Z,
+                      int64_t k, double* times) {
+  BK_TRY(enter(ctx, "bk_debug_twostage"));
+  BK_REQUIRE(A && d && e && n > 0 && fits_int(n) && k >= 0 && k <= n, "bk_debug_twostage: bad arguments");
+  DevBuf<double> dA, dd, de, dZ;
+  BK_TRY(h2d(ctx, dA, A, (size_t)n * n));
+  BK_TRY(dd.alloc(n));
+  BK_TRY(de.alloc(n));
+  BK_CUDA(cudaMemsetAsync(de.p, 0, sizeof(double) * n, ctx->stream));
+  TwoStage ts;
+  if (band) {
+    // stage 1 only, then copy the band out before stage 2 destroys it
+    const int b = sy2sb_bandwidth(), npan = (int)ceil_div(n, b);
+    DevBuf<double> w, ab, tst;
+    BK_TRY(w.alloc((size_t)n * n));
+    BK_TRY(ab.alloc((size_t)2 * b * n));
+    BK_TRY(tst.alloc((size_t)npan * b * b));
+    BK_TRY(copy_matrix(ctx, dA.p, n, (int)n, (int)n, 1.0, w.p, n));
+    BK_TRY(sy2sb(ctx, w.p, n, (int)n, tst.p, ab.p, 2 * b));
+    BK_TRY(d2h(ctx, band, ab.p, (size_t)2 * b * n));
+  }
+  BK_TRY(twostage_reduce(ctx, dA.p, n, (int)n, &ts, dd.p, de.p));
+  BK_TRY(d2h(ctx, d, dd.p, n));
+  if (n > 1) BK_TRY(d2h(ctx, e, de.p, n - 1));
+  if (Z && k > 0) {
+    // Z (n x k, host, column-major): in = tridiagonal eigenvectors, out = Q1 Q2 Z
+    BK_TRY(h2d(ctx, dZ, Z, (size_t)n * k));
+    BK_TRY(twostage_back(ctx, &ts, dZ.p, n, (int)k));
+    BK_TRY(d2h(ctx, Z, dZ.p, (size_t)n * k));
+  }
+  if (times) {
+    times[0] = ts.t_sy2sb;
+    times[1] = ts.t_sb2st;
+    times[2] = ts.t_q2;
+    times[3] = ts.t_q1;
+  }
+  return BK_OK;
+}
+
 int bk_debug_stedc(bk_ctx* ctx, const double* d, const double* e, int64_t n, double* evals, double* Z) {
   BK_TRY(enter(ctx, "bk_debug_stedc"));
   BK_REQUIRE(d && e && evals && n > 0 && fits_int(n), "bk_debug_stedc: bad arguments");

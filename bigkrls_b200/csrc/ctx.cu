@@ -374,7 +374,7 @@ int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result
   return BK_ERR_ARG;
 }
 
-int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower,
+int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower, double beta,
                    int iters, double* seconds) {
   BK_REQUIRE(ctx && seconds && m > 0 && n > 0 && k > 0, "bk_dgemm_bench: bad arguments");
   BK_CUDA(cudaSetDevice(ctx->device));
@@ -388,12 +388,11 @@ int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k,
   bk::Timer tm;
   BK_TRY(tm.init(ctx->stream));
   if (iters <= 0) iters = 3;
-  BK_TRY(bk::gemm(ctx, ta != 0, tb != 0, (int)m, (int)n, (int)k, 1.0, A.p, lda, B.p, ldb, 0.0, C.p, m,
-                  lower != 0));
+  BK_CUDA(cudaMemsetAsync(C.p, 0, sizeof(double) * (size_t)m * n, ctx->stream));
+  BK_TRY(bk::gemm(ctx, ta != 0, tb != 0, (int)m, (int)n, (int)k, 1e-3, A.p, lda, B.p, ldb, beta, C.p, m, lower));
   tm.start();
   for (int i = 0; i < iters; ++i)
-    BK_TRY(bk::gemm(ctx, ta != 0, tb != 0, (int)m, (int)n, (int)k, 1.0, A.p, lda, B.p, ldb, 0.0, C.p,
-                    m, lower != 0));
+    BK_TRY(bk::gemm(ctx, ta != 0, tb != 0, (int)m, (int)n, (int)k, 1e-3, A.p, lda, B.p, ldb, beta, C.p, m, lower));
   *seconds = tm.stop() / iters;
   return BK_OK;
 }

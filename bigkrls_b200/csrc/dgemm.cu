@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(WM* WN * 32)
   static_assert((size_t)CW * LDS <= (size_t)STAGES * (A_STAGE + B_STAGE), "staging tile must fit");
   double* Cs = smem;
   const bool vecC = ((((uintptr_t)C) & 15u) == 0) && (ldc % 2 == 0);
+  const bool mirror = (pr.lower == 2) && (n0 + BN - 1 < m0);  // tile strictly below the diagonal
 #pragma unroll
   for (int chunk = 0; chunk < BN / CW; ++chunk) {
     const int c_lo = chunk * CW;
@@ -228,9 +229,26 @@ __global__ void __launch_bounds__(WM* WN * 32)
           o.y += beta * old.y;
         }
         *reinterpret_cast<double2*>(cp) = o;
+        if (mirror) {
+          Cs[cc * LDS + 2 * rp] = o.x;
+          Cs[cc * LDS + 2 * rp + 1] = o.y;
+        }
       } else {
         cp[0] = (beta != 0.0) ? v0 + beta * cp[0] : v0;
-        if (row + 1 < pr.m) cp[1] = (beta != 0.0) ? v1 + beta * cp[1] : v1;
+        if (mirror) Cs[cc * LDS + 2 * rp] = cp[0];
+        if (row + 1 < pr.m) {
+          cp[1] = (beta != 0.0) ? v1 + beta * cp[1] : v1;
+          if (mirror) Cs[cc * LDS + 2 * rp + 1] = cp[1];
+        }
+      }
+    }
+    if (mirror) {
+      // transposed copy of the finished tile: C[col, row], contiguous along the tile's columns
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < BM * CW; idx += NT) {
+        const int cc = idx % CW, rr = idx / CW;
+        const int row = m0 + rr, col = n0 + c_lo + cc;
+        if (row < pr.m && col < pr.n) C[col + (long long)row * ldc] = Cs[cc * LDS + rr];
       }
     }
     if (chunk + 1 < BN / CW) __syncthreads();
@@ -317,7 +335,7 @@ int gemm_batched(bk_ctx* ctx, bool ta, bool tb, const GemmProb* dprobs, int npro
 
 int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
          long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
-         bool lower) {
+         int lower) {
   if (m <= 0 || n <= 0) return BK_OK;
   GemmProb p;
   p.A = A;
@@ -331,19 +349,26 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
   p.ldc = ldc;
   p.alpha = alpha;
   p.beta = beta;
-  p.lower = lower ? 1 : 0;
+  p.lower = lower;
   const bool vec = gemm_operands_vec_ok(A, lda, B, ldb);
 
   int bm, bn;
   if (n <= 32) {
     bm = 128;
     bn = 32;
-  } else if (m <= 64 || n <= 64) {
+  } else if (m <= 64) {
     bm = 64;
+    bn = 64;
+  } else if (n <= 64) {
+    bm = 128;  // tall-and-64-wide (block-reflector products of the two-stage reduction)
     bn = 64;
   } else {
     bm = 128;
     bn = 128;
+    // short-k read-modify-write updates are bound by the C traffic of the epilogue: the 128x64 tile runs
+    // two CTAs per SM so that one CTA's epilogue overlaps the other's main loop
+    static const int rmw64 = getenv("BK_GEMM_RMW64") ? atoi(getenv("BK_GEMM_RMW64")) : 1;
+    if (rmw64 && beta != 0.0 && k <= 256) bn = 64;
   }
   const int tiles = (int)(ceil_div(m, bm) * ceil_div(n, bn));
   // deterministic split-K when the tile grid cannot fill the machine and k is long
@@ -360,6 +385,8 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
   int rc;
   if (bn == 32)
     rc = dispatch<128, 32, 8, 1>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
+  else if (bm == 128 && bn == 64)
+    rc = dispatch<128, 64, 4, 2>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
   else if (bm == 64)
     rc = dispatch<64, 64, 2, 4>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
   else

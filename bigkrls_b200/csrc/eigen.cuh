@@ -38,6 +38,8 @@ struct EigenTimes {
   double tridiag = 0, dc = 0, backtransform = 0;
   StedcStats dc_stats;
   SytrdStats sytrd;
+  int twostage = 0;
+  double t_sy2sb = 0, t_sb2st = 0, t_q2 = 0, t_q1 = 0;
 };
 
 // Full path: K (n x n symmetric, device, preserved) -> evals_host[n] DESCENDING and the
@@ -45,6 +47,24 @@ struct EigenTimes {
 // is padded to a multiple of 16 doubles (aligned columns for the TMA bulk copies of sytrd).
 int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host, int max_want,
                double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times);
+// Two-stage tridiagonalisation (sy2sb.cu, sb2st.cu): dense -> band (b = 64) -> tridiagonal, and the
+// back-transformation Z <- Q1 Q2 Z.  Cheaper than the one-stage reduction when few eigenvectors are wanted:
+// stage 1 is GEMM-bound, stage 2 works on the L2-resident band.
+int sy2sb_bandwidth();
+int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab);
+int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops);
+int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz, int k);
+int q1_apply(bk_ctx* ctx, const double* A, long long lda, int n, const double* Tstore, double* Z, long long ldz,
+             int k);
+struct TwoStage {
+  DevBuf<double> work, AB, Tstore, VV, TAU;
+  int maxhops = 0, n = 0;
+  double t_sy2sb = 0, t_sb2st = 0, t_q2 = 0, t_q1 = 0;
+};
+// K (n x n, only read) -> d, e (device, length n); reflectors kept in ts for twostage_back
+int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e);
+int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k);
+bool use_twostage(int n, int max_want);
 inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
 
 // Top-k eigenpairs (k << n) by restarted block Krylov + Rayleigh-Ritz (eigen_topk.cu): evals_host[k]

@@ -90,10 +90,61 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
   return BK_OK;
 }
 
+static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host,
+                               int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
+                               EigenTimes* times) {
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  DevBuf<double> d, e;
+  BK_TRY(d.alloc(n));
+  BK_TRY(e.alloc(n));
+  BK_CUDA(cudaMemsetAsync(e.p, 0, sizeof(double) * n, ctx->stream));
+  TwoStage ts;
+  tm.start();
+  BK_TRY(twostage_reduce(ctx, K, ldk, n, &ts, d.p, e.p));
+  const double t_tri = tm.stop();
+  std::vector<double> dh(n), eh(n), ev(n);
+  BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(dh[i]) || !std::isfinite(eh[i])) {
+      set_error("eigen: tridiagonalisation produced a non-finite entry (NaN/Inf in the input?)");
+      return BK_ERR_NUMERIC;
+    }
+  tm.start();
+  int nw = 0;
+  StedcStats st;
+  BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
+  const double t_dc = tm.stop();
+  tm.start();
+  if (Z && nw > 0) BK_TRY(twostage_back(ctx, &ts, Z, ldz, nw));
+  const double t_bt = tm.stop();
+  if (getenv("BK_EIG_VERBOSE"))
+    fprintf(stderr, "[eigen2 n=%d] sy2sb %.4f sb2st %.4f | dc %.4f | q2 %.4f q1 %.4f (k=%d)\n", n, ts.t_sy2sb,
+            ts.t_sb2st, t_dc, ts.t_q2, ts.t_q1, nw);
+  for (int i = 0; i < n; ++i) evals_host[i] = ev[n - 1 - i];
+  if (n_want) *n_want = nw;
+  if (times) {
+    times->tridiag = t_tri;
+    times->dc = t_dc;
+    times->backtransform = t_bt;
+    times->dc_stats = st;
+    times->sytrd = SytrdStats();
+    times->twostage = 1;
+    times->t_sy2sb = ts.t_sy2sb;
+    times->t_sb2st = ts.t_sb2st;
+    times->t_q2 = ts.t_q2;
+    times->t_q1 = ts.t_q1;
+  }
+  return BK_OK;
+}
+
 int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host, int max_want,
                double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times) {
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
+  if (use_twostage(n, Z ? max_want : 0)) return eigen_full_twostage(ctx, K, ldk, n, evals_host, max_want, rel_thresh, n_want, Z, ldz, times);
   DevBuf<double> d, e, tau, workbuf;
   const long long ldw = sytrd_ld(n);
   BK_TRY(workbuf.alloc((size_t)ldw * n));

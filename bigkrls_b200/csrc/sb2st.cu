@@ -1,0 +1,650 @@
+// Two-stage tridiagonalisation, stage 2: symmetric band (bandwidth b = 64) -> tridiagonal by bulge chasing,
+// and the back-transformation of eigenvectors through both stages.
+// Executable specification: tests/twostage_prototype.py (sb2st, apply_q2, apply_q1).
+//
+// Bulge chasing (chase_kernel).  Sweep j annihilates column j below the sub-diagonal with a Householder
+// reflector of length <= b and chases the bulge down the band in hops of b rows: per hop a two-sided update
+// of a b x b diagonal block, a right-update of the b x b block below it, and a new reflector that removes the
+// first column of the bulge.  Sweeps are pipelined: one CTA per sweep, sweep j may execute hop t once
+// sweep j-1 has finished hop t+1 (progress counters in global memory, acquire/release) - about n/(2b)
+// sweeps are in flight, which matches the SM count at the target size.  The band lives in L2 (n x 2b doubles).
+//
+// Q2 back-transformation (q2_apply_kernel).  The reflector (sweep j, hop t) acts on rows
+// [j+1+tb, j+1+(t+1)b).  For a fixed hop index t the row window slides up by ONE row per sweep, so a CTA that
+// owns hop index t keeps the 64 x k window of Z in SHARED MEMORY for all sweeps, loads one new row and
+// retires one finished row per sweep.  CTA t consumes the rows retired by CTA t-1 (flag per hop index), so the
+// whole back-transformation is a software pipeline over hop indices with no grid barrier.
+#include <climits>
+#include <cstdlib>
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "eigen.cuh"
+#include "kernels.cuh"
+
+namespace bk {
+
+static constexpr int CB = 64;        // bandwidth
+static constexpr int LDAB = 2 * CB;  // working band storage (bulges reach 2b-1 below the diagonal)
+static constexpr int CH_NT = 256;
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+struct ChaseArgs {
+  double* AB;     // LDAB x n
+  int n;
+  double* VV;     // n x n (ld n): column j holds the reflectors of sweep j at their row positions
+  double* TAU;    // maxhops x n
+  int maxhops;
+  int* prog;      // n: hops completed by sweep j (INT_MAX when finished)
+  double* d;
+  double* e;
+};
+
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory"); }
+
+// Householder scalars from alpha = x[0] and s = |x[1:]|^2: (I - tau v v') x = beta e1, v = [1, x[1:] * scale]
+__device__ __forceinline__ void house_scalars(double alpha, double s, double& beta, double& tau, double& scale) {
+  if (s == 0.0) {
+    beta = alpha;
+    tau = 0.0;
+    scale = 0.0;
+  } else {
+    beta = -copysign(sqrt(alpha * alpha + s), alpha);
+    tau = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+}
+
+// The CTA is split into two groups of 128 threads that work concurrently inside a hop: group A owns the
+// reflector chain (block below the diagonal block: right-update, new reflector, left-update), group B the
+// two-sided update of the diagonal block.  Both hold their 64 x 64 block in registers (32 doubles per
+// thread: row r = thread % 64, columns cq, cq+2, ...) and use shared memory only for the reductions.
+__global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
+  extern __shared__ __align__(16) double chase_sm[];
+  double (*Ds)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chase_sm);
+  double (*Bs)[CB + 1] = Ds + CB;
+  __shared__ double v[CB], v2[CB], w[CB], wa[CB];
+  __shared__ double pA[2][CB], pD[2][CB], redA[4], redB[4];
+  __shared__ double s_alpha, s_tau0, s_tau2;
+  const int n = a.n;
+  double* AB = a.AB;
+  const int tid = threadIdx.x;
+  const int grp = tid >> 7, gt = tid & 127, gw = gt >> 5, lane = tid & 31;
+  const int r = gt & (CB - 1), cq = gt >> 6;
+  for (int j = blockIdx.x; j < n - 2; j += gridDim.x) {
+    double tau = 0.0;
+    for (int t = 0;; ++t) {
+      const int lo = j + 1 + t * CB;
+      if (lo >= n) break;
+      const int hi = min(n, lo + CB), L = hi - lo;
+      if (t == 0 && L < 2) break;
+      const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
+      // ---- wait until sweep j-1 is two hops ahead (also orders the v <- v2 copy of the previous hop) -------
+      if (j > 0 && tid == 0) {
+        while (ld_acquire_i32(a.prog + j - 1) < t + 2) {
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      // ---- every global load of the hop is issued up front ------------------------------------------------
+      double x[32];
+      double colv = 0.0;
+      if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = cq + 2 * i;
+          const int dd = L + r - c;  // row hi+r, column lo+c
+          x[i] = (r < L2 && c < L && dd < LDAB) ? __ldcg(AB + dd + (size_t)(lo + c) * LDAB) : 0.0;
+        }
+        if (t == 0 && gt < L) colv = __ldcg(AB + (1 + gt) + (size_t)j * LDAB);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = cq + 2 * i;
+          x[i] = (r >= c && r < L) ? __ldcg(AB + (r - c) + (size_t)(lo + c) * LDAB) : 0.0;
+        }
+      }
+      if (t == 0) {
+        // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
+        if (grp == 0) {
+          double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redA[gw] = s;
+          if (gt == 0) s_alpha = colv;
+          group_bar(1);
+          double beta, tau0, scale;
+          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
+          if (gt < L) v[gt] = (gt == 0) ? 1.0 : colv * scale;
+          if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
+          if (gt == 0) {
+            AB[1 + (size_t)j * LDAB] = beta;
+            a.e[j] = beta;
+            a.d[j] = __ldcg(AB + (size_t)j * LDAB);
+            s_tau0 = tau0;
+          }
+        }
+        __syncthreads();
+        tau = s_tau0;
+      }
+      const bool has_b = hi < n;
+      const bool more = has_b && (L2 >= 2);
+      if (grp == 1) {
+        // ================= group B: two-sided update of D = A[lo:hi, lo:hi] =================================
+        if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
+        if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = cq + 2 * i;
+          if (r >= c && r < L) {
+            Ds[r][c] = x[i];
+            Ds[c][r] = x[i];
+          }
+        }
+        group_bar(2);
+        {
+          // w = tau D v: half of the columns per thread, row r
+          double s = 0.0;
+          if (r < L) {
+            const int c0 = cq * 32, c1 = min(L, c0 + 32);
+            for (int c = c0; c < c1; ++c) s = fma(Ds[r][c], v[c], s);
+          }
+          pD[cq][r] = s;
+        }
+        group_bar(2);
+        {
+          const double wr0 = (gt < L) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
+          if (gt < CB) w[gt] = wr0;
+          double s = (gt < L) ? wr0 * v[gt] : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redB[gw] = s;
+        }
+        group_bar(2);
+        {
+          const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
+          const double vr = (r < L) ? v[r] : 0.0;
+          const double wr = (r < L) ? fma(al, vr, w[r]) : 0.0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            if (r >= c && r < L) {
+              const double vc = v[c], wc = fma(al, vc, w[c]);
+              AB[(r - c) + (size_t)(lo + c) * LDAB] = x[i] - vr * wc - wr * vc;
+            }
+          }
+        }
+      } else if (has_b) {
+        // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
+        {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            if (c < L) s = fma(x[i], v[c], s);
+          }
+          pA[cq][r] = s;
+        }
+        group_bar(1);
+        {
+          const double ur = tau * (pA[0][r] + pA[1][r]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            if (c < L) x[i] = fma(-ur, v[c], x[i]);
+          }
+        }
+        if (more) {
+          // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
+          double s = (cq == 0 && r >= 1 && r < L2) ? x[0] * x[0] : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redA[gw] = s;
+          if (gt == 0) s_alpha = x[0];
+          group_bar(1);
+          double beta, tau2, scale;
+          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
+          if (cq == 0) {
+            if (r < L2) v2[r] = (r == 0) ? 1.0 : x[0] * scale;
+            x[0] = (r == 0) ? beta : 0.0;
+          }
+          if (gt == 0) s_tau2 = tau2;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            if (r < L2 && c < L) Bs[r][c] = x[i];
+          }
+          group_bar(1);
+          {
+            // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
+            double s2 = 0.0;
+            if (r < L) {
+              const int q0 = cq * 32, q1 = min(L2, q0 + 32);
+              for (int q = q0; q < q1; ++q) s2 = fma(v2[q], Bs[q][r], s2);
+            }
+            pA[cq][r] = s2;
+          }
+          group_bar(1);
+          if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
+          group_bar(1);
+          {
+            const double v2r = (r < L2) ? v2[r] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              if (c >= 1 && c < L) x[i] = fma(-v2r, wa[c], x[i]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = cq + 2 * i;
+          const int dd = L + r - c;
+          if (r < L2 && c < L && dd < LDAB) AB[dd + (size_t)(lo + c) * LDAB] = x[i];
+        }
+      }
+      __syncthreads();
+      if (more) {
+        if (tid < L2) v[tid] = v2[tid];
+        tau = s_tau2;
+      }
+      if (tid == 128) {
+        __threadfence();
+        st_release_i32(a.prog + j, t + 1);
+      }
+      if (!more) break;
+    }
+    __syncthreads();
+    if (tid == 128) {
+      __threadfence();
+      st_release_i32(a.prog + j, INT_MAX);
+    }
+  }
+}
+
+// d[n-2], d[n-1], e[n-2] are never touched by a sweep with a reflector: read them off the band at the end
+__global__ void chase_tail_kernel(const double* __restrict__ AB, int n, double* d, double* e) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int j = max(0, n - 2); j < n; ++j) {
+      d[j] = AB[(size_t)j * LDAB];
+      if (j + 1 < n) e[j] = AB[1 + (size_t)j * LDAB];
+    }
+  }
+}
+
+int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops) {
+  DevBuf<int> prog;
+  BK_TRY(prog.alloc(n));
+  BK_CUDA(cudaMemsetAsync(prog.p, 0, sizeof(int) * n, ctx->stream));
+  ChaseArgs a;
+  a.AB = AB;
+  a.n = n;
+  a.VV = VV;
+  a.TAU = TAU;
+  a.maxhops = maxhops;
+  a.prog = prog.p;
+  a.d = d;
+  a.e = e;
+  if (n > 2) {
+    void* kargs[] = {&a};
+    const size_t smem = sizeof(double) * 2 * CB * (CB + 1);
+    BK_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctx->sm_count), dim3(CH_NT), kargs, smem,
+                                        ctx->stream));
+    BK_LAUNCHED(ctx);
+  }
+  chase_tail_kernel<<<1, 32, 0, ctx->stream>>>(AB, n, d, e);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Q2 back-transformation on Zt (k x n, row r of Z = column r of Zt, contiguous)
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int Q2_KC = 192;         // columns of Z per launch = compute threads (one column each)
+static constexpr int Q2_NT = Q2_KC + 64;  // + one warp that only polls / publishes the pipeline flags (+1 idle)
+static constexpr int Q2_R = 4;            // sweeps applied per pass over the window
+static constexpr int Q2_ROWS = 2 * CB;    // buffer rows: the window slides through the buffer, no wrap-around
+
+struct Q2Args {
+  double* Zt;     // kc x n (ld = ldzt)
+  long long ldzt;
+  int n, kc;
+  const double* VV;
+  const double* TAU;
+  int maxhops;
+  int* done;      // per hop index: lowest sweep already applied (INT_MAX initially)
+};
+
+// One CTA owns hop index t for all sweeps (j = jmax(t) .. 0).  The reflector (j, t) acts on rows
+// [j+1+64t, j+65+64t): the window slides up one row per sweep.  The window lives in a 128-row shared-memory
+// buffer (one column per compute thread) and slides towards row 0 of the buffer; when it gets there the
+// thread copies its 63 values back to the top (every ~64 sweeps), so every access uses a compile-time
+// offset from one moving base.  While the window is still growing (near the bottom of the matrix) and for
+// the last few sweeps a one-sweep-per-step path is used; in between every pass pulls the 63 resident rows
+// plus 4 new rows into registers, applies 4 consecutive reflectors and retires 4 rows, so that each window
+// element crosses shared memory once per 4 sweeps.  Rows retired by hop index t-1 are the rows entering the
+// window of hop index t: done[t-1] is the only synchronisation.
+__global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
+  extern __shared__ __align__(16) double win[];  // Q2_ROWS x Q2_KC
+  __shared__ __align__(16) double vs[2][Q2_R][CB];
+  __shared__ double taus[2][Q2_R];
+  const int n = a.n, kc = a.kc, tid = threadIdx.x;
+  const bool flagger = (tid == Q2_KC);  // lane 0 of the flag warp
+  const bool act = tid < kc;            // compute thread with a real column
+  const int nhop = (n - 3) / CB + 1;    // hop indices t with jmax(t) = n-3-t*CB >= 0
+  const double* VV = a.VV;
+  double* col = win + (tid < Q2_KC ? tid : 0);  // this thread's column: row q at col[q * Q2_KC]
+  for (int t = blockIdx.x; t < nhop; t += gridDim.x) {
+    const int jmax = n - 3 - t * CB;
+    const int jfull = n - CB - 1 - t * CB;  // largest sweep whose window is a full 64 rows
+    const int* pdone = a.done + t - 1;
+    int* mydone = a.done + t;
+    int j = jmax;
+    int p = CB;  // buffer row of the top row (lo) of the window of sweep j
+    // move the resident rows buf[p+1 .. p+cnt] to buf[CB+1 .. CB+cnt] (descending: the ranges may overlap)
+    auto rebase = [&](int cnt) {
+      if (act)
+        for (int i = cnt; i >= 1; --i) col[(CB + i) * Q2_KC] = col[(p + i) * Q2_KC];
+      p = CB;
+    };
+    // One sweep, window read from shared memory with run-time length (growing window / tail sweeps).
+    auto slow_sweep = [&](int js, bool first) {
+      const int lo = js + 1 + t * CB, hi = min(n, lo + CB), L = hi - lo;
+      if (p < 0) rebase(L - 1);
+      if (t > 0 && flagger) {
+        while (ld_acquire_i32(pdone) > js + 1) {
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      if (act) {
+        if (first) {
+          for (int i = 0; i < L; ++i) col[(p + i) * Q2_KC] = __ldcg(a.Zt + tid + (size_t)(lo + i) * a.ldzt);
+        } else {
+          col[p * Q2_KC] = __ldcg(a.Zt + tid + (size_t)lo * a.ldzt);
+        }
+      }
+      if (tid < L) vs[0][0][tid] = VV[(size_t)(lo + tid) + (size_t)js * n];
+      if (tid == 0) taus[0][0] = a.TAU[t + (size_t)js * a.maxhops];
+      __syncthreads();
+      if (act) {
+        double s0 = 0.0, s1 = 0.0;
+        int i = 0;
+        for (; i + 1 < L; i += 2) {
+          s0 = fma(vs[0][0][i], col[(p + i) * Q2_KC], s0);
+          s1 = fma(vs[0][0][i + 1], col[(p + i + 1) * Q2_KC], s1);
+        }
+        if (i < L) s0 = fma(vs[0][0][i], col[(p + i) * Q2_KC], s0);
+        const double wv = taus[0][0] * (s0 + s1);
+        for (i = 0; i < L; ++i) col[(p + i) * Q2_KC] -= vs[0][0][i] * wv;
+        if (lo + CB <= n) a.Zt[tid + (size_t)(lo + CB - 1) * a.ldzt] = col[(p + CB - 1) * Q2_KC];
+      }
+      __syncthreads();
+      if (flagger) {
+        __threadfence();
+        st_release_i32(mydone, js);
+      }
+      --p;
+    };
+    // ---- phase 1: the window grows from 2 to 63 rows ------------------------------------------------------
+    for (; j >= 0 && j > jfull; --j) slow_sweep(j, j == jmax);
+    // ---- phase 2: full window, Q2_R sweeps per pass ---------------------------------------------------------
+    if (j >= Q2_R - 1) {
+      // loads for a pass starting at sweep jp: its 4 new rows and its 4 reflectors
+      double pr[Q2_R], vreg = 0.0, treg = 0.0;
+      auto issue_pass_loads = [&](int jp) {
+        const int lo = jp + 1 + t * CB;
+#pragma unroll
+        for (int s = 0; s < Q2_R; ++s) pr[s] = act ? __ldcg(a.Zt + tid + (size_t)(lo - s) * a.ldzt) : 0.0;
+        if (tid < Q2_R * CB) {
+          const int s = tid >> 6, i = tid & (CB - 1);
+          vreg = VV[(size_t)(lo - s + i) + (size_t)(jp - s) * n];
+        }
+        if (tid < Q2_R) treg = a.TAU[t + (size_t)(jp - tid) * a.maxhops];
+      };
+      // a pass at sweep jp needs hop index t-1 to have applied sweep jp-2
+      auto wait_pass = [&](int jp) {
+        if (t > 0 && flagger) {
+          while (ld_acquire_i32(pdone) > jp - 2) {
+          }
+          __threadfence();
+        }
+      };
+      wait_pass(j);
+      if (j - Q2_R >= Q2_R - 1) wait_pass(j - Q2_R);
+      __syncthreads();
+      issue_pass_loads(j);
+      int cur = 0;
+      if (tid < Q2_R * CB) vs[cur][tid >> 6][tid & (CB - 1)] = vreg;
+      if (tid < Q2_R) taus[cur][tid] = treg;
+      double z[CB + Q2_R - 1];
+#pragma unroll
+      for (int s = 0; s < Q2_R; ++s) z[Q2_R - 1 - s] = pr[s];  // z[i] <-> row lo-3+i <-> buffer row p-3+i
+      __syncthreads();
+      while (j >= Q2_R - 1) {
+        const int lo = j + 1 + t * CB;
+        const bool have_next = (j - Q2_R >= Q2_R - 1);
+        if (have_next) issue_pass_loads(j - Q2_R);  // verified before the previous barrier
+        if (p < Q2_R - 1) rebase(CB - 1);
+        if (act) {
+          double* wb = col + (p - (Q2_R - 1)) * Q2_KC;
+#pragma unroll
+          for (int i = Q2_R; i < CB + Q2_R - 1; ++i) z[i] = wb[i * Q2_KC];
+#pragma unroll
+          for (int s = 0; s < Q2_R; ++s) {
+            const int off = Q2_R - 1 - s;
+            const double2* v2p = reinterpret_cast<const double2*>(&vs[cur][s][0]);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < CB; i += 4) {
+              const double2 va = v2p[i / 2], vb = v2p[i / 2 + 1];
+              s0 = fma(va.x, z[off + i], s0);
+              s1 = fma(va.y, z[off + i + 1], s1);
+              s2 = fma(vb.x, z[off + i + 2], s2);
+              s3 = fma(vb.y, z[off + i + 3], s3);
+            }
+            const double wv = taus[cur][s] * ((s0 + s1) + (s2 + s3));
+#pragma unroll
+            for (int i = 0; i < CB; i += 2) {
+              const double2 va = v2p[i / 2];
+              z[off + i] = fma(-va.x, wv, z[off + i]);
+              z[off + i + 1] = fma(-va.y, wv, z[off + i + 1]);
+            }
+          }
+          // retire the 4 bottom rows, keep the other 63 in the window
+          double* zt = a.Zt + tid + (size_t)(lo - (Q2_R - 1)) * a.ldzt;
+#pragma unroll
+          for (int i = CB - 1; i < CB + Q2_R - 1; ++i) zt[(size_t)i * a.ldzt] = z[i];
+#pragma unroll
+          for (int i = 0; i < CB - 1; ++i) wb[i * Q2_KC] = z[i];
+        }
+        p -= Q2_R;
+        if (have_next) {
+          if (tid < Q2_R * CB) vs[cur ^ 1][tid >> 6][tid & (CB - 1)] = vreg;
+          if (tid < Q2_R) taus[cur ^ 1][tid] = treg;
+#pragma unroll
+          for (int s = 0; s < Q2_R; ++s) z[Q2_R - 1 - s] = pr[s];
+          if (j - 2 * Q2_R >= Q2_R - 1) wait_pass(j - 2 * Q2_R);
+        }
+        __syncthreads();
+        if (flagger) {
+          __threadfence();
+          st_release_i32(mydone, j - (Q2_R - 1));
+        }
+        cur ^= 1;
+        j -= Q2_R;
+      }
+    }
+    // ---- phase 3: the last (< Q2_R) sweeps ----------------------------------------------------------------
+    for (; j >= 0; --j) slow_sweep(j, false);
+    // flush what is left of the window (nobody inside this kernel waits for these rows): after the last
+    // sweep p points one above the row of lo0 = 1 + 64 t
+    {
+      const int lo0 = 1 + t * CB;
+      const int cnt = ((lo0 + CB <= n) ? lo0 + CB - 1 : n) - lo0;
+      if (act)
+        for (int i = 0; i < cnt; ++i) a.Zt[tid + (size_t)(lo0 + i) * a.ldzt] = col[(p + 1 + i) * Q2_KC];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void transpose_kernel(const double* __restrict__ src, long long lds, int rows, int cols,
+                                 double* __restrict__ dst, long long ldd) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int r = r0 + tx, c = c0 + cc;
+    tile[cc][tx] = (r < rows && c < cols) ? src[r + (long long)c * lds] : 0.0;
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int c = c0 + tx, r = r0 + rr;  // dst(c, r) = src(r, c)
+    if (r < rows && c < cols) dst[c + (long long)r * ldd] = tile[tx][rr];
+  }
+}
+
+// Z (n x k, ld ldz) <- Q2 Z
+int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz,
+             int k) {
+  if (n < 3 || k <= 0) return BK_OK;
+  const int nhop = (n - 3) / CB + 1;
+  DevBuf<double> Zt;
+  DevBuf<int> done;
+  const int nchunk = (int)ceil_div(k, Q2_KC);
+  const int KC = (int)ceil_div(k, nchunk);  // balanced column chunks, each <= Q2_KC
+  BK_TRY(Zt.alloc((size_t)KC * n));
+  BK_TRY(done.alloc(nhop));
+  BK_CUDA(cudaFuncSetAttribute(q2_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * Q2_ROWS * Q2_KC)));
+  for (int k0 = 0; k0 < k; k0 += KC) {
+    const int kc = std::min(KC, k - k0);
+    dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(kc, 32));
+    transpose_kernel<<<tg, 256, 0, ctx->stream>>>(Z + (size_t)k0 * ldz, ldz, n, kc, Zt.p, kc);
+    BK_LAUNCHED(ctx);
+    std::vector<int> init(nhop, INT_MAX);
+    BK_CUDA(cudaMemcpyAsync(done.p, init.data(), sizeof(int) * nhop, cudaMemcpyHostToDevice, ctx->stream));
+    Q2Args a;
+    a.Zt = Zt.p;
+    a.ldzt = kc;
+    a.n = n;
+    a.kc = kc;
+    a.VV = VV;
+    a.TAU = TAU;
+    a.maxhops = maxhops;
+    a.done = done.p;
+    void* kargs[] = {&a};
+    const int G = std::min(ctx->sm_count, nhop);
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)q2_apply_kernel, dim3(G), dim3(Q2_NT), kargs,
+                                        sizeof(double) * Q2_ROWS * Q2_KC, ctx->stream));
+    BK_LAUNCHED(ctx);
+    dim3 tg2((unsigned)ceil_div(kc, 32), (unsigned)ceil_div(n, 32));
+    transpose_kernel<<<tg2, 256, 0, ctx->stream>>>(Zt.p, kc, kc, n, Z + (size_t)k0 * ldz, ldz);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Q1 back-transformation: block reflectors of stage 1, last panel first
+// ---------------------------------------------------------------------------------------------------------
+__global__ void unpack_panel_v_kernel(const double* __restrict__ A, long long lda, int r0, int c0, int b, int m,
+                                      double* __restrict__ Vb) {
+  const long long total = (long long)m * b;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % m), c = (int)(idx / m);
+    double v;
+    if (r < c || c >= m - 1)
+      v = 0.0;  // above the diagonal, or no reflector for this column
+    else if (r == c)
+      v = 1.0;
+    else
+      v = A[(long long)(r0 + r) + (long long)(c0 + c) * lda];
+    Vb[r + (long long)c * m] = v;
+  }
+}
+
+int q1_apply(bk_ctx* ctx, const double* A, long long lda, int n, const double* Tstore, double* Z, long long ldz,
+             int k) {
+  const int b = CB;
+  DevBuf<double> Vb, W1, W2;
+  BK_TRY(Vb.alloc((size_t)n * b));
+  BK_TRY(W1.alloc((size_t)b * k));
+  BK_TRY(W2.alloc((size_t)b * k));
+  int npan = 0;
+  for (int c0 = 0; c0 < n; c0 += b) {
+    if (n - (c0 + b) < 2) break;
+    ++npan;
+  }
+  for (int p = npan - 1; p >= 0; --p) {
+    const int c0 = p * b, r0 = c0 + b, m = n - r0;
+    const long long tot = (long long)m * b;
+    unpack_panel_v_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 256), 8LL * ctx->sm_count), 256, 0, ctx->stream>>>(
+        A, lda, r0, c0, b, m, Vb.p);
+    BK_LAUNCHED(ctx);
+    const double* Tk = Tstore + (size_t)p * b * b;
+    double* Zr = Z + r0;
+    BK_TRY(gemm(ctx, true, false, b, k, m, 1.0, Vb.p, m, Zr, ldz, 0.0, W1.p, b));
+    BK_TRY(gemm(ctx, false, false, b, k, b, 1.0, Tk, b, W1.p, b, 0.0, W2.p, b));
+    BK_TRY(gemm(ctx, false, false, m, k, b, -1.0, Vb.p, m, W2.p, b, 1.0, Zr, ldz));
+  }
+  BK_CUDA(cudaGetLastError());
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e) {
+  const int b = CB;
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  ts->n = n;
+  ts->maxhops = n / b + 2;
+  const int npan = (int)ceil_div(n, b);
+  BK_TRY(ts->work.alloc((size_t)n * n));
+  BK_TRY(ts->AB.alloc((size_t)LDAB * n));
+  BK_TRY(ts->Tstore.alloc((size_t)npan * b * b));
+  BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
+  BK_CUDA(cudaMemsetAsync(ts->TAU.p, 0, sizeof(double) * (size_t)ts->maxhops * n, ctx->stream));
+  tm.start();
+  BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, ts->work.p, n));
+  BK_TRY(sy2sb(ctx, ts->work.p, n, n, ts->Tstore.p, ts->AB.p, LDAB));
+  ts->t_sy2sb = tm.stop();
+  BK_TRY(ts->VV.alloc((size_t)n * n));
+  tm.start();
+  BK_TRY(sb2st(ctx, ts->AB.p, n, d, e, ts->VV.p, ts->TAU.p, ts->maxhops));
+  ts->t_sb2st = tm.stop();
+  return BK_OK;
+}
+
+int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k) {
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  tm.start();
+  BK_TRY(q2_apply(ctx, ts->VV.p, ts->TAU.p, ts->maxhops, ts->n, Z, ldz, k));
+  ts->t_q2 = tm.stop();
+  tm.start();
+  BK_TRY(q1_apply(ctx, ts->work.p, ts->n, ts->n, ts->Tstore.p, Z, ldz, k));
+  ts->t_q1 = tm.stop();
+  return BK_OK;
+}
+
+// Two-stage pays off when the back-transformation is narrow (the Q2 pass costs ~2 n^2 k flops at low
+// arithmetic intensity) and the matrix is large enough for the GEMM-bound stage 1 to beat the SYMV-bound
+// one-stage panels.
+bool use_twostage(int n, int max_want) {
+  if (const char* f = getenv("BK_EIG_TWOSTAGE")) return atoi(f) != 0;
+  return n >= 4096 && n <= 56000 && max_want <= n / 8;
+}
+
+}  // namespace bk

@@ -1,0 +1,241 @@
+// Two-stage tridiagonalisation, stage 1: dense symmetric -> band (bandwidth b = 64).
+// Executable specification: tests/twostage_prototype.py (sy2sb).  Together with sb2st.cu this replaces the
+// one-stage reduction of sytrd.cu when only part of the eigenvectors is wanted: all O(N^3) work becomes
+// DMMA GEMMs (the one-stage algorithm is bound by an HBM-resident symmetric mat-vec per column).
+//
+// Per panel (columns c0 .. c0+b-1, rows r0 = c0+b .. n-1, m = n - r0):
+//   1. Householder QR of the m x b panel in ONE cooperative kernel: the panel is distributed by row
+//      slabs over the CTAs and stays in SHARED MEMORY for all b columns; per column one grid barrier
+//      (partial dot products of the pivot column with the remaining columns -> every CTA forms tau and
+//      the update coefficients redundantly -> updates its own slab).
+//   2. T (compact WY) from V'V;  Z = A22 (V T);  W = Z - 1/2 V (T' (V'Z));  A22 -= [V W][W V]'
+//      on the DMMA GEMM - 6 m^2 b flops per panel, 2 N^3 in total.
+// The matrix is kept fully symmetric (both triangles updated) so that A22 (V T) is a plain GEMM.
+// V is left LAPACK-style below the band of A (unit diagonal implicit) and T_k is stored for the
+// back-transformation.
+#include <cstdlib>
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "eigen.cuh"
+#include "kernels.cuh"
+
+namespace bk {
+
+static constexpr int SB = 64;     // bandwidth / panel width
+static constexpr int QR_NT = 256;
+
+struct PanelArgs {
+  double* A;        // n x n, lda
+  long long lda;
+  int n, c0;
+  double* V;        // explicit V, rows r0.., ld = ldv (two copies: V and V2)
+  double* V2;
+  long long ldv;
+  double* taus;     // SB
+  double* part;     // [2][G][SB]
+  double* prow;     // [2][SB]
+  unsigned* barrier;
+  int rows_per;
+};
+
+__global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
+  extern __shared__ __align__(16) double slab[];  // rows_per x (SB+1)
+  __shared__ double s_dots[SB], s_prow[SB];
+  constexpr int LD = SB + 1;
+  const int n = a.n, r0 = a.c0 + SB, m = n - r0;
+  const int G = gridDim.x;
+  const int row_lo = blockIdx.x * a.rows_per;              // local (panel) row range of this CTA
+  const int nrows = max(0, min(a.rows_per, m - row_lo));
+  const int nr = min(SB, m - 1);                           // reflectors
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned epoch = 0;
+
+  for (int idx = threadIdx.x; idx < nrows * SB; idx += QR_NT) {
+    const int r = idx % nrows, l = idx / nrows;
+    slab[r * LD + l] = a.A[(long long)(r0 + row_lo + r) + (long long)(a.c0 + l) * a.lda];
+  }
+  __syncthreads();
+
+  for (int j = 0; j < nr; ++j) {
+    const int buf = j & 1;
+    double* part = a.part + (size_t)buf * G * SB;
+    double* prow = a.prow + buf * SB;
+    // ---- partial sums over own rows strictly below the pivot row j -----------------------------------
+    const int rs = max(0, j + 1 - row_lo);  // first own local row with panel row > j
+    for (int l = j + warp; l < SB; l += QR_NT / 32) {
+      double s = 0.0;
+      for (int r = rs + lane; r < nrows; r += 32) s = fma(slab[r * LD + j], slab[r * LD + l], s);
+      s = warp_sum(s);
+      if (lane == 0) part[(size_t)blockIdx.x * SB + l] = s;
+    }
+    if (j >= row_lo && j < row_lo + nrows) {
+      for (int l = j + threadIdx.x; l < SB; l += QR_NT) prow[l] = slab[(j - row_lo) * LD + l];
+    }
+    grid_barrier(a.barrier, epoch);
+    // ---- every CTA: totals, reflector, update coefficients ---------------------------------------------
+    {
+      const int l = j + (threadIdx.x >> 2), sub = threadIdx.x & 3;
+      double s = 0.0;
+      if (l < SB)
+        for (int c = sub; c < G; c += 4) s += __ldcg(part + (size_t)c * SB + l);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (l < SB && sub == 0) {
+        s_dots[l] = s;
+        s_prow[l] = __ldcg(prow + l);
+      }
+    }
+    __syncthreads();
+    const double alpha = s_prow[j], xnorm2 = s_dots[j];
+    double beta, tau, scale;
+    if (xnorm2 == 0.0) {
+      beta = alpha;
+      tau = 0.0;
+      scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.taus[j] = tau;
+    // own rows below the pivot: P[r,l] -= v_r * t_l, then column j becomes v
+    for (int idx = threadIdx.x; idx < (nrows - rs) * (SB - j - 1); idx += QR_NT) {
+      const int r = rs + idx / (SB - j - 1), l = j + 1 + idx % (SB - j - 1);
+      const double tl = tau * (s_prow[l] + scale * s_dots[l]);
+      slab[r * LD + l] -= (scale * slab[r * LD + j]) * tl;
+    }
+    __syncthreads();
+    for (int r = rs + threadIdx.x; r < nrows; r += QR_NT) slab[r * LD + j] *= scale;
+    if (j >= row_lo && j < row_lo + nrows) {  // pivot row: v = 1
+      for (int l = j + 1 + threadIdx.x; l < SB; l += QR_NT)
+        slab[(j - row_lo) * LD + l] -= tau * (s_prow[l] + scale * s_dots[l]);
+      if (threadIdx.x == 0) slab[(j - row_lo) * LD + j] = beta;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0)
+    for (int l = nr + threadIdx.x; l < SB; l += QR_NT) a.taus[l] = 0.0;
+  // ---- write back: LAPACK-style into A, explicit unit-lower-trapezoidal V (two copies) ----------------
+  for (int idx = threadIdx.x; idx < nrows * SB; idx += QR_NT) {
+    const int r = idx % nrows, l = idx / nrows;
+    const int pr = row_lo + r;  // panel row
+    const double x = slab[r * LD + l];
+    a.A[(long long)(r0 + pr) + (long long)(a.c0 + l) * a.lda] = x;
+    double v = 0.0;
+    if (l < nr) v = (pr > l) ? x : (pr == l ? 1.0 : 0.0);
+    a.V[(long long)(r0 + pr) + (long long)l * a.ldv] = v;
+    a.V2[(long long)(r0 + pr) + (long long)l * a.ldv] = v;
+  }
+}
+
+// T (ib x ib upper triangular) from S = V'V and tau (same recurrence as ormtr.cu)
+__global__ void sb_larft_kernel(const double* __restrict__ S, const double* __restrict__ tau, int ib,
+                                double* __restrict__ T) {
+  extern __shared__ double ts[];  // T (ib x ib) then S (ib x ib)
+  double* ss = ts + ib * ib;
+  const int r = threadIdx.x;
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) {
+    ts[idx] = 0.0;
+    ss[idx] = S[idx];
+  }
+  __syncthreads();
+  for (int i = 0; i < ib; ++i) {
+    const double ti = tau[i];
+    double acc = 0.0;
+    if (r < i)
+      for (int q = r; q < i; ++q) acc = fma(ts[r + q * ib], ss[q + i * ib], acc);
+    __syncthreads();
+    if (r < i) ts[r + i * ib] = -ti * acc;
+    if (r == i) ts[i + i * ib] = ti;
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[idx];
+}
+
+// AB[d + j*ldab] = A[j+d, j] for d <= b, 0 for b < d < ldab   (lower band, working width 2b)
+__global__ void extract_band_kernel(const double* __restrict__ A, long long lda, int n, int b,
+                                    double* __restrict__ AB, int ldab) {
+  const long long total = (long long)n * ldab;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % ldab), j = (int)(idx / ldab);
+    double v = 0.0;
+    if (d <= b && j + d < n) v = A[(long long)(j + d) + (long long)j * lda];
+    AB[idx] = v;
+  }
+}
+
+int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab) {
+  const int b = SB;
+  BK_REQUIRE(ldab >= 2 * b, "sy2sb: band storage needs 2b rows");
+  const int G = ctx->sm_count;
+  DevBuf<double> P3, taus, part, prow, S, T, VT, S2, S3;
+  BK_TRY(P3.alloc((size_t)3 * b * n));
+  BK_TRY(taus.alloc(b));
+  BK_TRY(part.alloc((size_t)2 * G * b));
+  BK_TRY(prow.alloc(2 * b));
+  BK_TRY(S.alloc(b * b));
+  BK_TRY(T.alloc(b * b));
+  BK_TRY(VT.alloc((size_t)n * b));
+  BK_TRY(S2.alloc(b * b));
+  BK_TRY(S3.alloc(b * b));
+  BK_TRY(ctx->barrier.ensure(4));
+  const int max_rows_per = (int)ceil_div(std::max(1, n - b), G);
+  const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
+  BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
+  BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  BK_CUDA(cudaFuncSetAttribute(sb_larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * 2 * b * b)));
+  static const bool full_update = getenv("BK_SY2SB_FULL") != nullptr;
+  BK_CUDA(cudaMemsetAsync(P3.p, 0, sizeof(double) * (size_t)3 * b * n, ctx->stream));
+  int k = 0;
+  for (int c0 = 0; c0 < n; c0 += b, ++k) {
+    const int r0 = c0 + b, m = n - r0;
+    if (m < 2) break;
+    double* V = P3.p;                     // [V | W | V], ld n, rows r0.. used
+    double* W = P3.p + (size_t)b * n;
+    double* V2 = P3.p + (size_t)2 * b * n;
+    PanelArgs pa;
+    pa.A = A;
+    pa.lda = lda;
+    pa.n = n;
+    pa.c0 = c0;
+    pa.V = V;
+    pa.V2 = V2;
+    pa.ldv = n;
+    pa.taus = taus.p;
+    pa.part = part.p;
+    pa.prow = prow.p;
+    pa.barrier = ctx->barrier.p;
+    pa.rows_per = (int)ceil_div(m, G);
+    BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
+    void* kargs[] = {&pa};
+    const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(G), dim3(QR_NT), kargs, smem, ctx->stream));
+    BK_LAUNCHED(ctx);
+    double* Vr = V + r0;
+    double* Wr = W + r0;
+    double* A22 = A + r0 + (long long)r0 * lda;
+    double* Tk = Tstore + (size_t)k * b * b;
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vr, n, Vr, n, 0.0, S.p, b));
+    sb_larft_kernel<<<1, b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
+    BK_LAUNCHED(ctx);
+    BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vr, n, Tk, b, 0.0, VT.p, m));               // V T
+    BK_TRY(gemm(ctx, false, false, m, b, m, 1.0, A22, lda, VT.p, m, 0.0, Wr, n));             // Z = A22 V T
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vr, n, Wr, n, 0.0, S2.p, b));                 // V'Z
+    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));               // T' V'Z
+    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, Vr, n, S3.p, b, 1.0, Wr, n));               // W = Z - V S3 / 2
+    // A22 -= [V W][W V]': lower tiles computed, mirrored into the upper triangle by the epilogue
+    BK_TRY(gemm(ctx, false, true, m, m, 2 * b, -1.0, Vr, n, Wr, n, 1.0, A22, lda, full_update ? 0 : 2));
+  }
+  extract_band_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * ldab, 256), 16LL * ctx->sm_count), 256, 0,
+                        ctx->stream>>>(A, lda, n, b, AB, ldab);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BK_OK;
+}
+
+int sy2sb_bandwidth() { return SB; }
+
+}  // namespace bk

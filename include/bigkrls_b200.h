@@ -216,8 +216,9 @@ BK_API int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, doubl
  * kind 0: DFMA issue-bound loop, 1: DMMA m8n8k4 loop, 2: HBM copy.  Returns TFLOP/s or GB/s. */
 BK_API int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result);
 /* Time (device seconds, CUDA events) of `iters` runs of the library DGEMM on device-
- * generated data: C(m x n) = op(A) op(B). */
-BK_API int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower,
+ * generated data: C(m x n) = alpha op(A) op(B) + beta C; lower = 1 computes only the tiles on/below the
+ * diagonal, lower = 2 additionally mirrors them into the upper triangle. */
+BK_API int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower, double beta,
                    int iters, double* seconds);
 
 /* Stage-level hooks of the eigensolver (tests/test_gpu_eigen_stages.py): tridiagonalisation only
@@ -228,6 +229,11 @@ BK_API int bk_debug_gemm(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int6
                   int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower,
                   int repeats);
 BK_API int bk_debug_sytrd(bk_ctx* ctx, const double* A, int64_t n, double* d, double* e);
+/* Two-stage reduction (dense -> band -> tridiagonal).  band (optional, 128 x n) receives the stage-1 band in
+ * lower storage band[d + j*128] = B[j+d, j]; d/e the tridiagonal; Z (optional, n x k): on entry eigenvectors of
+ * the tridiagonal, on exit Q1 Q2 Z; times (optional, 4): seconds of sy2sb, sb2st, Q2, Q1. */
+BK_API int bk_debug_twostage(bk_ctx* ctx, const double* A, int64_t n, double* band, double* d, double* e, double* Z,
+                             int64_t k, double* times);
 BK_API int bk_debug_stedc(bk_ctx* ctx, const double* d, const double* e, int64_t n, double* evals, double* Z);
 
 /* ---- host-logic hooks (pure CPU, no device needed) ------------------------------------------

@@ -1,0 +1,73 @@
+"""Two-stage tridiagonalisation (sy2sb.cu / sb2st.cu) against numpy/LAPACK on the host (GPU).
+
+Checks each stage separately: the stage-1 band has the spectrum of K, the stage-2 tridiagonal has the
+spectrum of K, and the back-transformed eigenvectors diagonalise K.  Tolerances: eigenvalues 1e-12 relative
+to the largest (the product tolerance is 1e-9), residual / orthogonality 1e-12.
+"""
+import numpy as np
+import pytest
+from scipy.linalg import eigh_tridiagonal
+
+import krls_oracle as o
+from bigkrls_b200 import _lib
+from bigkrls_b200._lib import check, dptr
+
+pytestmark = pytest.mark.gpu
+
+
+def kernel_matrix(n, p, seed=5):
+    X, y = o.synthetic(n, p, seed)
+    Xs, *_ = o.standardize(X, y)
+    return np.asfortranarray(o.gauss_kernel(Xs, p))
+
+
+def band_to_dense(band, n, b):
+    B = np.zeros((n, n))
+    for d in range(b + 1):
+        idx = np.arange(n - d)
+        B[idx + d, idx] = band[d, idx]
+        B[idx, idx + d] = band[d, idx]
+    return B
+
+
+@pytest.mark.parametrize("n,p,k", [(3, 3, 3), (66, 3, 66), (130, 3, 130), (517, 6, 100), (1000, 4, 1000),
+                                    (3001, 5, 400)])
+def test_twostage(ctx, n, p, k):
+    lib = _lib.load()
+    A = kernel_matrix(n, p)
+    band = np.zeros((128, n), order="F")
+    d = np.zeros(n)
+    e = np.zeros(n)
+    ref = np.linalg.eigvalsh(A)
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, dptr(band), dptr(d), dptr(e), None, 0, None))
+    # stage 1
+    assert np.all(band[65:, :] == 0.0)
+    Bd = band_to_dense(band, n, 64)
+    assert np.max(np.abs(np.linalg.eigvalsh(Bd) - ref)) < 1e-12 * ref.max()
+    # stage 2
+    lam, S = eigh_tridiagonal(d, e[:n - 1]) if n > 1 else (d.copy(), np.ones((1, 1)))
+    assert np.max(np.abs(lam - ref)) < 1e-12 * ref.max()
+    # back-transformation of the top-k eigenvectors
+    Z = np.asfortranarray(S[:, n - k:])
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), dptr(Z), k, None))
+    resid = np.max(np.abs(A @ Z - Z * lam[n - k:]))
+    orth = np.max(np.abs(Z.T @ Z - np.eye(k)))
+    assert resid < 1e-12 * ref.max() * np.sqrt(n), resid
+    assert orth < 1e-12 * np.sqrt(n), orth
+
+
+def test_twostage_matches_onestage_fit(ctx, monkeypatch):
+    """The product path gives the same fit with either tridiagonalisation (tolerances of the north star)."""
+    from bigkrls_b200 import api
+    X, y = o.synthetic(4500, 4, 11)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("BK_EIG_TWOSTAGE", flag)
+        fit = api.bigKRLS(y, X, eigtrunc=0.001, ctx=ctx, noisy=False)
+        out[flag] = (fit["lambda"], np.array(fit["coeffs"]).ravel().copy(), np.array(fit["derivatives"]).copy(),
+                     fit["lastkeeper"])
+        fit.release_device()
+    assert out["0"][3] == out["1"][3]
+    assert abs(out["0"][0] - out["1"][0]) <= 1e-9 * abs(out["0"][0])
+    assert np.max(np.abs(out["0"][1] - out["1"][1])) <= 1e-8 * np.max(np.abs(out["0"][1]))
+    assert np.max(np.abs(out["0"][2] - out["1"][2])) <= 1e-8 * np.max(np.abs(out["0"][2]))

@@ -15,7 +15,7 @@ N, P = int(sys.argv[1]), int(sys.argv[2])
 kw = {}
 if len(sys.argv) > 3:
     kw["eigtrunc"] = float(sys.argv[3])
-reps = 1 if (len(sys.argv) > 4 and sys.argv[4] == "once") else 2
+reps = 1 if (len(sys.argv) > 4 and sys.argv[4] == "once") else int(os.environ.get("FIT_REPS", "2"))
 if len(sys.argv) > 5:
     kw["Neig"] = int(sys.argv[5])
 if len(sys.argv) > 6:

@@ -24,7 +24,7 @@ shapes = [(0, 1, 8192, 8192, 8192, 0), (0, 0, 8192, 8192, 8192, 0), (1, 0, 8192,
           (1, 0, 2000, 10, 20000, 0), (0, 0, 16384, 2048, 64, 0), (1, 0, 64, 2048, 16384, 0)]
 out["dgemm"] = []
 for ta, tb, m, n, k, lower in shapes:
-    _lib.check(lib.bk_dgemm_bench(ctx.handle, ta, tb, m, n, k, lower, 3, C.byref(r)))
+    _lib.check(lib.bk_dgemm_bench(ctx.handle, ta, tb, m, n, k, lower, 0.0, 3, C.byref(r)))
     flops = 2.0 * m * n * k * (0.5 if lower else 1.0)
     out["dgemm"].append({"ta": ta, "tb": tb, "m": m, "n": n, "k": k, "lower": lower, "sec": r.value,
                          "tflops": flops / r.value * 1e-12})

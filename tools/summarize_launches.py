@@ -12,7 +12,10 @@ tot = defaultdict(lambda: [0, 0.0])
 for r in rd:
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    name = re.sub(r"<.*", "", r["Kernel Name"]).split("(")[0]
+    name = r["Kernel Name"].split("(")[0]
+    if not (len(sys.argv) > 2 and sys.argv[2] == "full"):
+        name = re.sub(r"<.*", "", name)
+    name = name.replace("bk::", "").replace("void ", "")
     v = float(r["Metric Value"].replace(",", ""))
     unit = r.get("Metric Unit", "ns")
     scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(unit, 1e-9)
