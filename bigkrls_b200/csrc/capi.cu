@@ -26,7 +26,7 @@ int enter(bk_ctx* ctx, const char* fn) {
     set_error("%s: ctx is NULL", fn);
     return BK_ERR_ARG;
   }
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   return BK_OK;
 }
 bool fits_int(int64_t v) { return v >= 0 && v < 2147483647LL; }

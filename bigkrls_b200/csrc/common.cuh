@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string>
 #include <vector>
@@ -38,26 +39,56 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // RAII device buffer (doubles unless stated).  Allocation failures surface as BK_ERR_CUDA.
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) on the stream of
+// the context bound to the calling thread: repeated fits reuse the cached blocks instead of paying the
+// map/unmap cost of cudaMalloc/cudaFree for multi-GB matrices.  BK_NO_POOL=1 switches back to cudaMalloc.
+inline cudaStream_t& alloc_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+inline bool pool_enabled() {
+  static const bool on = (getenv("BK_NO_POOL") == nullptr);
+  return on;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t pool_stream = nullptr;  // stream the block was allocated on (stream-ordered pool)
+  bool pooled = false;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      // stream-ordered free: the block returns to the pool once the work queued so far has used it
+      if (!pooled || cudaFreeAsync(p, pool_stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+      }
+    }
     p = nullptr;
     n = 0;
+    pooled = false;
   }
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    cudaError_t e;
+    if (pool_enabled()) {
+      pool_stream = alloc_stream();
+      e = cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream);
+      pooled = (e == cudaSuccess);
+    } else {
+      e = cudaMalloc((void**)&p, count * sizeof(T));
+    }
     if (e != cudaSuccess) {
       p = nullptr;
-      set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      pooled = false;
+      cudaGetLastError();
+      set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
       return BK_ERR_CUDA;
     }
     n = count;
@@ -109,6 +140,12 @@ struct bk_ctx {
 };
 
 namespace bk {
+
+// makes ctx the current context of the calling thread: device + allocation stream
+inline cudaError_t bind_ctx(bk_ctx* c) {
+  alloc_stream() = c->stream;
+  return cudaSetDevice(c->device);
+}
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -45,18 +45,32 @@ int bk_init(int device, bk_ctx** out) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   BK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   BK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (bk::pool_enabled()) {
+    // keep freed blocks cached in the device's default pool (trimmed again in bk_destroy)
+    cudaMemPool_t pool;
+    BK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    BK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  bk::alloc_stream() = c->stream;
   *out = c;
   return BK_OK;
 }
 
 void bk_destroy(bk_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  bk::bind_ctx(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   ctx->gemm_ws.release();
   ctx->barrier.release();
   ctx->scratch.release();
+  cudaStreamSynchronize(ctx->stream);
+  if (bk::pool_enabled()) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
+  if (bk::alloc_stream() == ctx->stream) bk::alloc_stream() = nullptr;
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -65,7 +79,7 @@ void bk_destroy(bk_ctx* ctx) {
 int bk_device_info(bk_ctx* ctx, char* name, int name_len, int* sm_count, int64_t* hbm_total,
                    int64_t* hbm_free) {
   BK_REQUIRE(ctx != nullptr, "bk_device_info: ctx is NULL");
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   cudaDeviceProp prop;
   BK_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
   if (name && name_len > 0) {
@@ -84,7 +98,7 @@ int64_t bk_launch_count(bk_ctx* ctx) { return ctx ? (int64_t)ctx->n_launches : 0
 
 int bk_host_alloc(bk_ctx* ctx, int64_t bytes, void** out) {
   BK_REQUIRE(ctx && out && bytes > 0, "bk_host_alloc: bad arguments");
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   BK_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
   return BK_OK;
 }
@@ -277,7 +291,7 @@ extern "C" {
 
 int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result) {
   BK_REQUIRE(ctx && result, "bk_microbench: bad arguments");
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   bk::Timer tm;
   BK_TRY(tm.init(ctx->stream));
   bk::DevBuf<double> buf;
@@ -377,7 +391,7 @@ int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result
 int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower, double beta,
                    int iters, double* seconds) {
   BK_REQUIRE(ctx && seconds && m > 0 && n > 0 && k > 0, "bk_dgemm_bench: bad arguments");
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   bk::DevBuf<double> A, B, C;
   BK_TRY(A.alloc((size_t)m * k));
   BK_TRY(B.alloc((size_t)k * n));

@@ -64,7 +64,7 @@ struct TwoStage {
 // K (n x n, only read) -> d, e (device, length n); reflectors kept in ts for twostage_back
 int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e);
 int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k);
-bool use_twostage(int n, int max_want);
+bool use_twostage(int n, int max_want, double rel_thresh);
 inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
 
 // Top-k eigenpairs (k << n) by restarted block Krylov + Rayleigh-Ritz (eigen_topk.cu): evals_host[k]

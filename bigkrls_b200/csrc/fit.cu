@@ -514,7 +514,7 @@ int create_fit(bk_ctx* ctx, const double* Xs, const double* ys, bool on_device, 
   if (comm && comm->world > 1)
     BK_REQUIRE(comm->allreduce_sum && comm->allgatherv && comm->broadcast,
                "bk_fit_run: communicator callbacks missing");
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   bk_fit* f = new bk_fit();
   f->ctx = ctx;
   f->n = (int)n;
@@ -559,7 +559,7 @@ int get_block(const bk_fit* f, const DevBuf<double>& buf, bool have, double* hos
     return BK_ERR_STATE;
   }
   bk_ctx* ctx = f->ctx;
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   const size_t cnt = (size_t)f->n * (size_t)(f->c1 - f->c0);
   // single-GPU fits hold the full matrix; multi-GPU fits hold only the owned block (Vc, Vf) or
   // the full K (offset to the owned block)
@@ -571,7 +571,7 @@ int get_block(const bk_fit* f, const DevBuf<double>& buf, bool have, double* hos
 int get_vec(const bk_fit* f, const double* dev, size_t cnt, double* host) {
   BK_REQUIRE(f && host && dev, "getter: NULL argument or field not computed");
   bk_ctx* ctx = f->ctx;
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   BK_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   return BK_OK;
@@ -609,7 +609,7 @@ int bk_fit_run_device(bk_ctx* ctx, const double* dXs, const double* dys, int64_t
 }
 void bk_fit_free(bk_fit* f) {
   if (!f) return;
-  cudaSetDevice(f->ctx->device);
+  bk::bind_ctx(f->ctx);
   cudaStreamSynchronize(f->ctx->stream);
   delete f;
 }
@@ -683,7 +683,7 @@ int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred
                    double* se2) {
   BK_REQUIRE(f && newXs && pred_std && m > 0 && m < 2147483647LL, "bk_fit_predict: bad arguments");
   bk_ctx* ctx = f->ctx;
-  BK_CUDA(cudaSetDevice(ctx->device));
+  BK_CUDA(bk::bind_ctx(ctx));
   const int n = f->n, p = f->p, k = f->k, mi = (int)m;
   DevBuf<double> dN, dK, dp;
   BK_TRY(dN.alloc((size_t)m * p));

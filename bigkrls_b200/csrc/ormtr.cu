@@ -90,9 +90,11 @@ int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double
   return BK_OK;
 }
 
+// *too_wide is set (and nothing is written) when the eigenvalue threshold keeps so many eigenvectors that the
+// one-stage reduction with its GEMM-bound back-transformation is the cheaper way to get them.
 static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals_host,
                                int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
-                               EigenTimes* times) {
+                               EigenTimes* times, bool* too_wide) {
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
   DevBuf<double> d, e;
@@ -117,6 +119,10 @@ static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int 
   StedcStats st;
   BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
   const double t_dc = tm.stop();
+  if (Z && nw > n / 3 && !getenv("BK_EIG_TWOSTAGE")) {
+    *too_wide = true;
+    return BK_OK;
+  }
   tm.start();
   if (Z && nw > 0) BK_TRY(twostage_back(ctx, &ts, Z, ldz, nw));
   const double t_bt = tm.stop();
@@ -144,7 +150,11 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
                double rel_thresh, int* n_want, double* Z, long long ldz, EigenTimes* times) {
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
-  if (use_twostage(n, Z ? max_want : 0)) return eigen_full_twostage(ctx, K, ldk, n, evals_host, max_want, rel_thresh, n_want, Z, ldz, times);
+  if (use_twostage(n, Z ? max_want : 0, rel_thresh)) {
+    bool too_wide = false;
+    BK_TRY(eigen_full_twostage(ctx, K, ldk, n, evals_host, max_want, rel_thresh, n_want, Z, ldz, times, &too_wide));
+    if (!too_wide) return BK_OK;
+  }
   DevBuf<double> d, e, tau, workbuf;
   const long long ldw = sytrd_ld(n);
   BK_TRY(workbuf.alloc((size_t)ldw * n));

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       if (j > 0 && tid == 0) {
         while (ld_acquire_i32(a.prog + j - 1) < t + 2) {
         }
-        __threadfence();
       }
       __syncthreads();
       // ---- every global load of the hop is issued up front ------------------------------------------------
@@ -150,12 +149,14 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
         group_bar(2);
         {
           // w = tau D v: half of the columns per thread, row r
-          double s = 0.0;
+          double sa[4] = {0.0, 0.0, 0.0, 0.0};
           if (r < L) {
-            const int c0 = cq * 32, c1 = min(L, c0 + 32);
-            for (int c = c0; c < c1; ++c) s = fma(Ds[r][c], v[c], s);
+            const int c0 = cq * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c0 + c < L) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
           }
-          pD[cq][r] = s;
+          pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
         }
         group_bar(2);
         {
@@ -182,13 +183,13 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       } else if (has_b) {
         // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
         {
-          double s = 0.0;
+          double sa[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int c = cq + 2 * i;
-            if (c < L) s = fma(x[i], v[c], s);
+            if (c < L) sa[i & 3] = fma(x[i], v[c], sa[i & 3]);
           }
-          pA[cq][r] = s;
+          pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
         }
         group_bar(1);
         {
@@ -221,12 +222,14 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
           group_bar(1);
           {
             // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
-            double s2 = 0.0;
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
             if (r < L) {
-              const int q0 = cq * 32, q1 = min(L2, q0 + 32);
-              for (int q = q0; q < q1; ++q) s2 = fma(v2[q], Bs[q][r], s2);
+              const int q0 = cq * 32;
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (q0 + q < L2) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
             }
-            pA[cq][r] = s2;
+            pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
           }
           group_bar(1);
           if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
@@ -252,17 +255,11 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
         if (tid < L2) v[tid] = v2[tid];
         tau = s_tau2;
       }
-      if (tid == 128) {
-        __threadfence();
-        st_release_i32(a.prog + j, t + 1);
-      }
+      if (tid == 128) st_release_i32(a.prog + j, t + 1);  // release is cumulative over the CTA barrier
       if (!more) break;
     }
     __syncthreads();
-    if (tid == 128) {
-      __threadfence();
-      st_release_i32(a.prog + j, INT_MAX);
-    }
+    if (tid == 128) st_release_i32(a.prog + j, INT_MAX);
   }
 }
 
@@ -361,7 +358,6 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
       if (t > 0 && flagger) {
         while (ld_acquire_i32(pdone) > js + 1) {
         }
-        __threadfence();
       }
       __syncthreads();
       if (act) {
@@ -387,10 +383,7 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
         if (lo + CB <= n) a.Zt[tid + (size_t)(lo + CB - 1) * a.ldzt] = col[(p + CB - 1) * Q2_KC];
       }
       __syncthreads();
-      if (flagger) {
-        __threadfence();
-        st_release_i32(mydone, js);
-      }
+      if (flagger) st_release_i32(mydone, js);
       --p;
     };
     // ---- phase 1: the window grows from 2 to 63 rows ------------------------------------------------------
@@ -414,7 +407,6 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
         if (t > 0 && flagger) {
           while (ld_acquire_i32(pdone) > jp - 2) {
           }
-          __threadfence();
         }
       };
       wait_pass(j);
@@ -441,16 +433,17 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
           for (int s = 0; s < Q2_R; ++s) {
             const int off = Q2_R - 1 - s;
             const double2* v2p = reinterpret_cast<const double2*>(&vs[cur][s][0]);
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            double sa[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < CB; i += 4) {
               const double2 va = v2p[i / 2], vb = v2p[i / 2 + 1];
-              s0 = fma(va.x, z[off + i], s0);
-              s1 = fma(va.y, z[off + i + 1], s1);
-              s2 = fma(vb.x, z[off + i + 2], s2);
-              s3 = fma(vb.y, z[off + i + 3], s3);
+              const int q = i & 4;
+              sa[q] = fma(va.x, z[off + i], sa[q]);
+              sa[q + 1] = fma(va.y, z[off + i + 1], sa[q + 1]);
+              sa[q + 2] = fma(vb.x, z[off + i + 2], sa[q + 2]);
+              sa[q + 3] = fma(vb.y, z[off + i + 3], sa[q + 3]);
             }
-            const double wv = taus[cur][s] * ((s0 + s1) + (s2 + s3));
+            const double wv = taus[cur][s] * (((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7])));
 #pragma unroll
             for (int i = 0; i < CB; i += 2) {
               const double2 va = v2p[i / 2];
@@ -474,10 +467,7 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
           if (j - 2 * Q2_R >= Q2_R - 1) wait_pass(j - 2 * Q2_R);
         }
         __syncthreads();
-        if (flagger) {
-          __threadfence();
-          st_release_i32(mydone, j - (Q2_R - 1));
-        }
+        if (flagger) st_release_i32(mydone, j - (Q2_R - 1));
         cur ^= 1;
         j -= Q2_R;
       }
@@ -642,9 +632,11 @@ int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k) {
 // Two-stage pays off when the back-transformation is narrow (the Q2 pass costs ~2 n^2 k flops at low
 // arithmetic intensity) and the matrix is large enough for the GEMM-bound stage 1 to beat the SYMV-bound
 // one-stage panels.
-bool use_twostage(int n, int max_want) {
+bool use_twostage(int n, int max_want, double rel_thresh) {
   if (const char* f = getenv("BK_EIG_TWOSTAGE")) return atoi(f) != 0;
-  return n >= 4096 && n <= 56000 && max_want <= n / 8;
+  // with a relative eigenvalue threshold (eigtrunc) the number of vectors is only known after the
+  // tridiagonal eigenvalues: go two-stage and let eigen_full fall back if the threshold keeps > n/3
+  return n >= 4096 && n <= 56000 && (max_want <= n / 8 || rel_thresh > 0.0);
 }
 
 }  // namespace bk
