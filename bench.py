@@ -13,9 +13,13 @@ the same synthetic workload (SURVEY.md 8d generator, seed 1003).
   e2e    seconds per fit through the public API bigKRLS(y, X) with HOST buffers: standardise,
          H2D of X/y, fit, D2H of every output field incl. the three N x N matrices (pinned
          host buffers from the library's pool)
-  roofline  dominant kernel = the tridiagonalisation panel kernel (symmetric mat-vec): algorithmic
-         bytes (lower triangle once per column: sum_j 4 (N-1-j)^2) / summed CUDA-event duration of
-         its launches, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  roofline  dominant kernel = the FP64 tensor-core (DMMA m8n8k4) GEMM of the dense->band stage of the two-stage
+         tridiagonalisation (per panel: Z = A22 (V T) and the symmetric rank-128 update): useful flops
+         (4 b m^2 per panel, the update counted on the lower triangle only) / summed CUDA-event duration of
+         those launches on the library stream, against the FP64 DMMA peak measured live by the library's
+         micro-benchmark (MEASURED_PEAKS.json only carries bf16, which an FP64 path cannot use).  When the
+         one-stage reduction is taken instead (all eigenvectors wanted) the dominant kernel is its HBM-bound
+         symmetric mat-vec panel kernel and the roofline is bytes against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the compiled literal restatement of the reference (oracle/krls_port.cpp, OpenBLAS,
          all host threads) on a bounded sample, scaled cubically to the metric's size
 
@@ -248,19 +252,49 @@ def main():
     if rank != 0:
         return
     info = infos[-1]
-    peak, peak_src = measured_peaks()
-    ach = info["sytrd_bytes"] / info["sytrd_kernel_seconds"] * 1e-9 if info["sytrd_kernel_seconds"] > 0 else 0.0
-    traffic, traffic_src = None, None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_sytrd_traffic.json")))
-        traffic = tr["traffic_over_algorithmic"] * info["sytrd_bytes"] / max(1.0, info["sytrd_launches"])
-        traffic_src = ("dram__bytes_read+write of one ncu --set full capture (launch 40, ratio %.3f to its algorithmic "
-                       "bytes) scaled to the average launch" % tr["traffic_over_algorithmic"])
-    except Exception:  # noqa: BLE001
-        pass
+    if info.get("twostage", 0) > 0:
+        r = C.c_double()
+        check(lib.bk_microbench(ctx.handle, 1, 0, 0, C.byref(r)))      # FP64 DMMA issue-bound loop, TFLOP/s
+        peak = float(r.value)
+        ach = info["band_gemm_flops"] / info["band_gemm_seconds"] * 1e-12 if info["band_gemm_seconds"] > 0 else 0.0
+        nl = max(1.0, info["band_gemm_launches"])
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_band_gemm_traffic.json")))
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        except Exception:  # noqa: BLE001
+            pass
+        roofline = {"kernel": "dgemm_kernel<128,64> (FP64 DMMA GEMM: Z = A22 (V T) and A22 -= [V W][W V]' of the "
+                              "dense->band stage)", "bound": "tensor", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_source": "FP64 mma.sync.m8n8k4 issue-bound loop measured live (bk_microbench kind 1); "
+                                   "MEASURED_PEAKS.json holds bf16/HBM only and bf16 is not usable at the 1e-9 "
+                                   "tolerance of this path",
+                    "launches_per_step": int(info["band_gemm_launches"]),
+                    "algorithmic_flops_per_launch": info["band_gemm_flops"] / nl,
+                    "avg_launch_seconds": info["band_gemm_seconds"] / nl,
+                    "share_of_step": info["band_gemm_seconds"] / info["t_total"],
+                    "traffic": traffic, "traffic_source": traffic_src}
+    else:
+        peak, peak_src = measured_peaks()
+        ach = info["sytrd_bytes"] / info["sytrd_kernel_seconds"] * 1e-9 if info["sytrd_kernel_seconds"] > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_sytrd_traffic.json")))
+            traffic = tr["traffic_over_algorithmic"] * info["sytrd_bytes"] / max(1.0, info["sytrd_launches"])
+            traffic_src = ("dram__bytes_read+write of one ncu --set full capture (launch 40, ratio %.3f to its "
+                           "algorithmic bytes) scaled to the average launch" % tr["traffic_over_algorithmic"])
+        except Exception:  # noqa: BLE001
+            pass
+        roofline = {"kernel": "sytrd_panel_kernel (symmetric mat-vec of the tridiagonalisation)", "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                    "launches_per_step": int(info["sytrd_launches"]),
+                    "algorithmic_bytes_per_launch": info["sytrd_bytes"] / max(1.0, info["sytrd_launches"]),
+                    "avg_launch_seconds": info["sytrd_kernel_seconds"] / max(1.0, info["sytrd_launches"]),
+                    "traffic": traffic, "traffic_source": traffic_src}
     stage = {k: float(np.mean([i[k] for i in infos])) for k in
-             ("t_kernel", "t_eigen", "t_tridiag", "t_dc", "t_backtransform", "t_lambda", "t_coef", "t_vcov",
-              "t_deriv", "t_total")}
+             ("t_kernel", "t_eigen", "t_tridiag", "t_sy2sb", "t_sb2st", "t_dc", "t_backtransform", "t_q2", "t_q1",
+              "t_lambda", "t_coef", "t_vcov", "t_deriv", "t_total")}
     line = {"metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -271,12 +305,7 @@ def main():
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "sytrd_panel_kernel (symmetric mat-vec of the tridiagonalisation)", "bound": "hbm",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                         "launches_per_step": int(info["sytrd_launches"]),
-                         "algorithmic_bytes_per_launch": info["sytrd_bytes"] / max(1.0, info["sytrd_launches"]),
-                         "avg_launch_seconds": info["sytrd_kernel_seconds"] / max(1.0, info["sytrd_launches"]),
-                         "traffic": traffic, "traffic_source": traffic_src},
+            "roofline": roofline,
             "stage_seconds": stage,
             "fit": {"lambda": info["lambda"], "lastkeeper": int(info["lastkeeper"]), "n_probes": info["n_probes"],
                     "n_passes": info["n_passes"], "dc_top_k": int(info["dc_top_k"])}}

@@ -60,7 +60,11 @@ class FitInfo(C.Structure):
                 ("sytrd_bytes", C.c_double),
                 ("dc_levels", C.c_double), ("dc_merge_flops", C.c_double), ("dc_top_n", C.c_double),
                 ("dc_top_k", C.c_double), ("gpu_launches", C.c_double),
-                ("krylov_matvecs", C.c_double), ("krylov_restarts", C.c_double)]
+                ("krylov_matvecs", C.c_double), ("krylov_restarts", C.c_double),
+                ("twostage", C.c_double), ("t_sy2sb", C.c_double), ("t_sb2st", C.c_double),
+                ("t_q2", C.c_double), ("t_q1", C.c_double),
+                ("band_gemm_launches", C.c_double), ("band_gemm_seconds", C.c_double),
+                ("band_gemm_flops", C.c_double)]
 
     def as_dict(self):
         d = {}

@@ -34,12 +34,19 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
 int ormtr_lower(bk_ctx* ctx, const double* A, long long lda, int n, const double* tau, double* Z,
                 long long ldz, int k);
 
+struct BandStats {
+  // the two large GEMMs of every stage-1 panel (Z = A22 (V T) and A22 -= [V W][W V]'): launches, summed CUDA-event
+  // time of those launches on the library stream, useful flops (the update counts the lower triangle once)
+  double gemm_launches = 0, gemm_seconds = 0, gemm_flops = 0;
+};
+
 struct EigenTimes {
   double tridiag = 0, dc = 0, backtransform = 0;
   StedcStats dc_stats;
   SytrdStats sytrd;
   int twostage = 0;
   double t_sy2sb = 0, t_sb2st = 0, t_q2 = 0, t_q1 = 0;
+  BandStats band;
 };
 
 // Full path: K (n x n symmetric, device, preserved) -> evals_host[n] DESCENDING and the
@@ -51,7 +58,8 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
 // back-transformation Z <- Q1 Q2 Z.  Cheaper than the one-stage reduction when few eigenvectors are wanted:
 // stage 1 is GEMM-bound, stage 2 works on the L2-resident band.
 int sy2sb_bandwidth();
-int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab);
+int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab,
+          BandStats* stats = nullptr);
 int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops);
 int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz, int k);
 int q1_apply(bk_ctx* ctx, const double* A, long long lda, int n, const double* Tstore, double* Z, long long ldz,
@@ -60,6 +68,7 @@ struct TwoStage {
   DevBuf<double> work, AB, Tstore, VV, TAU;
   int maxhops = 0, n = 0;
   double t_sy2sb = 0, t_sb2st = 0, t_q2 = 0, t_q1 = 0;
+  BandStats band;
 };
 // K (n x n, only read) -> d, e (device, length n); reflectors kept in ts for twostage_back
 int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e);

@@ -270,6 +270,14 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
       f->info.sytrd_launches = et.sytrd.launches;
       f->info.sytrd_kernel_seconds = et.sytrd.kernel_seconds;
       f->info.sytrd_bytes = et.sytrd.algorithmic_bytes;
+      f->info.twostage = et.twostage;
+      f->info.t_sy2sb = et.t_sy2sb;
+      f->info.t_sb2st = et.t_sb2st;
+      f->info.t_q2 = et.t_q2;
+      f->info.t_q1 = et.t_q1;
+      f->info.band_gemm_launches = et.band.gemm_launches;
+      f->info.band_gemm_seconds = et.band.gemm_seconds;
+      f->info.band_gemm_flops = et.band.gemm_flops;
       f->info.dc_levels = et.dc_stats.levels;
       f->info.dc_merge_flops = (double)et.dc_stats.merge_flops;
       f->info.dc_top_n = et.dc_stats.top_n;

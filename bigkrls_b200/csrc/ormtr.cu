@@ -142,6 +142,7 @@ static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int 
     times->t_sb2st = ts.t_sb2st;
     times->t_q2 = ts.t_q2;
     times->t_q1 = ts.t_q1;
+    times->band = ts.band;
   }
   return BK_OK;
 }

@@ -165,7 +165,7 @@ __global__ void extract_band_kernel(const double* __restrict__ A, long long lda,
   }
 }
 
-int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab) {
+int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab, BandStats* stats) {
   const int b = SB;
   BK_REQUIRE(ldab >= 2 * b, "sy2sb: band storage needs 2b rows");
   const int G = ctx->sm_count;
@@ -188,6 +188,16 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
                                (int)(sizeof(double) * 2 * b * b)));
   static const bool full_update = getenv("BK_SY2SB_FULL") != nullptr;
   BK_CUDA(cudaMemsetAsync(P3.p, 0, sizeof(double) * (size_t)3 * b * n, ctx->stream));
+  // CUDA events around the two large GEMMs of every panel (roofline of the dominant kernel, bench.py)
+  std::vector<cudaEvent_t> ev;
+  double flops = 0.0;
+  auto mark = [&]() {
+    if (!stats) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->stream);
+    ev.push_back(e);
+  };
   int k = 0;
   for (int c0 = 0; c0 < n; c0 += b, ++k) {
     const int r0 = c0 + b, m = n - r0;
@@ -221,18 +231,35 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     sb_larft_kernel<<<1, b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vr, n, Tk, b, 0.0, VT.p, m));               // V T
+    mark();
     BK_TRY(gemm(ctx, false, false, m, b, m, 1.0, A22, lda, VT.p, m, 0.0, Wr, n));             // Z = A22 V T
+    mark();
     BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vr, n, Wr, n, 0.0, S2.p, b));                 // V'Z
     BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));               // T' V'Z
     BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, Vr, n, S3.p, b, 1.0, Wr, n));               // W = Z - V S3 / 2
     // A22 -= [V W][W V]': lower tiles computed, mirrored into the upper triangle by the epilogue
+    mark();
     BK_TRY(gemm(ctx, false, true, m, m, 2 * b, -1.0, Vr, n, Wr, n, 1.0, A22, lda, full_update ? 0 : 2));
+    mark();
+    flops += 2.0 * m * (double)m * b + (full_update ? 2.0 : 1.0) * m * (double)m * 2 * b;
   }
   extract_band_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * ldab, 256), 16LL * ctx->sm_count), 256, 0,
                         ctx->stream>>>(A, lda, n, b, AB, ldab);
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    double sec = 0.0;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      sec += ms * 1e-3;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    stats->gemm_launches = (double)(ev.size() / 2);
+    stats->gemm_seconds = sec;
+    stats->gemm_flops = flops;
+  }
   return BK_OK;
 }
 

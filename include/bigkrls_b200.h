@@ -177,6 +177,12 @@ typedef struct bk_fit_info {
   double gpu_launches;
   /* Neig << N path (block Krylov): matrix-vector products with K and thick restarts (0 on the full path) */
   double krylov_matvecs, krylov_restarts;
+  /* two-stage tridiagonalisation (taken when few eigenvectors are wanted): 1 if used, device seconds of
+   * dense->band, band->tridiagonal, and the two back-transformations */
+  double twostage, t_sy2sb, t_sb2st, t_q2, t_q1;
+  /* its dominant kernel (the FP64 DMMA GEMM of the stage-1 panel updates): launches, summed CUDA-event time of
+   * those launches on the library stream, useful flops */
+  double band_gemm_launches, band_gemm_seconds, band_gemm_flops;
 } bk_fit_info;
 
 /* Xs (n x p) and ys (n) are the STANDARDISED data (R/bigKRLS.R:251-254), host pointers.
