@@ -329,8 +329,8 @@ int gemm_batched(bk_ctx* ctx, bool ta, bool tb, const GemmProb* dprobs, int npro
     const int tiles = (int)(ceil_div(max_m, 64) * ceil_div(max_n, 64));
     return dispatch<64, 64, 2, 4>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
   }
-  const int tiles = (int)(ceil_div(max_m, 128) * ceil_div(max_n, 128));
-  return dispatch<128, 128, 2, 4>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
+  const int tiles = (int)(ceil_div(max_m, 128) * ceil_div(max_n, 64));
+  return dispatch<128, 64, 4, 2>(ctx, ta, tb, vec, none, dprobs, nprob, tiles, 1, nullptr);
 }
 
 int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
@@ -363,12 +363,20 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
     bm = 128;  // tall-and-64-wide (block-reflector products of the two-stage reduction)
     bn = 64;
   } else {
+    // Measured on B200 (tools/gemm_shape_bench.py): residency beats tile size for FP64 DMMA.  128x64 tiles run
+    // two CTAs per SM (32.8 TF at 8192^3 against 29.1 TF for 128x128, one CTA per SM); for short k, where the
+    // prologue and the C traffic of the epilogue weigh most, 64x64 tiles with three CTAs per SM are best
+    // (rank-128 read-modify-write update: 22.8 TF against 18.9 / 13.2).
     bm = 128;
-    bn = 128;
-    // short-k read-modify-write updates are bound by the C traffic of the epilogue: the 128x64 tile runs
-    // two CTAs per SM so that one CTA's epilogue overlaps the other's main loop
-    static const int rmw64 = getenv("BK_GEMM_RMW64") ? atoi(getenv("BK_GEMM_RMW64")) : 1;
-    if (rmw64 && beta != 0.0 && k <= 256) bn = 64;
+    bn = 64;
+    if (k <= 256) bm = 64;
+  }
+  if (const char* f = getenv("BK_GEMM_FORCE")) {  // tuning experiments only
+    int fm = 0, fn = 0;
+    if (sscanf(f, "%dx%d", &fm, &fn) == 2 && ((fm == 128 && (fn == 128 || fn == 64 || fn == 32)) || (fm == 64 && fn == 64))) {
+      bm = fm;
+      bn = fn;
+    }
   }
   const int tiles = (int)(ceil_div(m, bm) * ceil_div(n, bn));
   // deterministic split-K when the tile grid cannot fill the machine and k is long
