@@ -222,12 +222,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
   __syncthreads();
   epoch += 1;
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release-add / acquire-load: cumulative over the CTA barrier above, no full (sc) fences needed
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
     const unsigned target = epoch * gridDim.x;
     while (ld_acquire_u32(counter) < target) {
     }
-    __threadfence();
   }
   __syncthreads();
 }

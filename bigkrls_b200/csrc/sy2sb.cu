@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
     grid_barrier(a.barrier, epoch);
     // ---- every CTA: totals, reflector, update coefficients ---------------------------------------------
     {
+      // each CTA keeps its partials in one contiguous 512-byte row (a transposed layout with coalesced
+      // reads was measured slower: 16 CTAs then share every line they write)
       const int l = j + (threadIdx.x >> 2), sub = threadIdx.x & 3;
       double s = 0.0;
       if (l < SB)
@@ -180,7 +182,10 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   BK_TRY(S2.alloc(b * b));
   BK_TRY(S3.alloc(b * b));
   BK_TRY(ctx->barrier.ensure(4));
-  const int max_rows_per = (int)ceil_div(std::max(1, n - b), G);
+  // Rows of the panel per CTA (lower bound; all SMs are used while m >= rows_target * SMs).  Measured: the
+  // per-column cost is dominated by the per-CTA slab work, not by the grid barrier - thin slabs win.
+  static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), G));
   const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
   BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
   BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -217,11 +222,12 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     pa.part = part.p;
     pa.prow = prow.p;
     pa.barrier = ctx->barrier.p;
-    pa.rows_per = (int)ceil_div(m, G);
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(G, ceil_div(m, rows_target)));
+    pa.rows_per = (int)ceil_div(m, Gp);
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
     void* kargs[] = {&pa};
     const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
-    BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(G), dim3(QR_NT), kargs, smem, ctx->stream));
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, ctx->stream));
     BK_LAUNCHED(ctx);
     double* Vr = V + r0;
     double* Wr = W + r0;
