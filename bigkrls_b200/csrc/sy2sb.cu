@@ -78,8 +78,18 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
       // reads was measured slower: 16 CTAs then share every line they write)
       const int l = j + (threadIdx.x >> 2), sub = threadIdx.x & 3;
       double s = 0.0;
-      if (l < SB)
-        for (int c = sub; c < G; c += 4) s += __ldcg(part + (size_t)c * SB + l);
+      if (l < SB) {
+        // 8 loads in flight per thread, summed in a fixed order
+        for (int c0 = sub; c0 < G; c0 += 32) {
+          double v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = c0 + 4 * q;
+            v[q] = (c < G) ? __ldcg(part + (size_t)c * SB + l) : 0.0;
+          }
+          s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+      }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       if (l < SB && sub == 0) {
