@@ -45,6 +45,7 @@ struct ChaseArgs {
   int* prog;      // n: hops completed by sweep j (INT_MAX when finished)
   double* d;
   double* e;
+  long long* prof;  // optional (BK_CHASE_PROF): [0] hops, [1] wait, [2] group A busy, [3] group B busy, [4] hop total
 };
 
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory"); }
@@ -86,12 +87,15 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       const int hi = min(n, lo + CB), L = hi - lo;
       if (t == 0 && L < 2) break;
       const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
+      long long tp0 = 0, tp1 = 0;
+      if (a.prof) tp0 = clock64();
       // ---- wait until sweep j-1 is two hops ahead (also orders the v <- v2 copy of the previous hop) -------
       if (j > 0 && tid == 0) {
         while (ld_acquire_i32(a.prog + j - 1) < t + 2) {
         }
       }
       __syncthreads();
+      if (a.prof) tp1 = clock64();
       // ---- every global load of the hop is issued up front ------------------------------------------------
       double x[32];
       double colv = 0.0;
@@ -250,7 +254,20 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
           if (r < L2 && c < L && dd < LDAB) AB[dd + (size_t)(lo + c) * LDAB] = x[i];
         }
       }
+      long long tp2 = 0;
+      if (a.prof) tp2 = clock64();
       __syncthreads();
+      if (a.prof && (tid == 0 || tid == 128) && blockIdx.x == 0) {
+        const long long tp3 = clock64();
+        if (tid == 0) {
+          a.prof[0] += 1;
+          a.prof[1] += tp1 - tp0;
+          a.prof[2] += tp2 - tp1;
+          a.prof[4] += tp3 - tp0;
+        } else {
+          a.prof[3] += tp2 - tp1;
+        }
+      }
       if (more) {
         if (tid < L2) v[tid] = v2[tid];
         tau = s_tau2;
@@ -286,6 +303,13 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   a.prog = prog.p;
   a.d = d;
   a.e = e;
+  DevBuf<long long> prof;
+  a.prof = nullptr;
+  if (getenv("BK_CHASE_PROF")) {
+    BK_TRY(prof.alloc(8));
+    BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+    a.prof = prof.p;
+  }
   if (n > 2) {
     void* kargs[] = {&a};
     const size_t smem = sizeof(double) * 2 * CB * (CB + 1);
@@ -298,6 +322,14 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (a.prof) {
+    long long h[8];
+    BK_CUDA(cudaMemcpyAsync(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double hops = (double)std::max(1LL, h[0]);
+    fprintf(stderr, "[chase prof, CTA 0] hops %lld: cycles per hop: wait %.0f, group A %.0f, group B %.0f, total %.0f\n",
+            h[0], h[1] / hops, h[2] / hops, h[3] / hops, h[4] / hops);
+  }
   return BK_OK;
 }
 
