@@ -336,10 +336,13 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
 // ---------------------------------------------------------------------------------------------------------
 // Q2 back-transformation on Zt (k x n, row r of Z = column r of Zt, contiguous)
 // ---------------------------------------------------------------------------------------------------------
-static constexpr int Q2_KC = 192;         // columns of Z per launch = compute threads (one column each)
-static constexpr int Q2_NT = Q2_KC + 64;  // + one warp that only polls / publishes the pipeline flags (+1 idle)
-static constexpr int Q2_R = 4;            // sweeps applied per pass over the window
-static constexpr int Q2_ROWS = 2 * CB;    // buffer rows: the window slides through the buffer, no wrap-around
+static constexpr int Q2_KC = 160;           // columns of Z per launch
+static constexpr int Q2_CT = 2 * Q2_KC;     // compute threads: two per column (upper / lower half of the window)
+static constexpr int Q2_NT = Q2_CT + 32;    // + one warp that only polls / publishes the pipeline flags
+static constexpr int Q2_R = 4;              // sweeps applied per pass over the window
+static constexpr int Q2_HALF = 34;          // window rows per thread: 2 * 34 >= 64 + Q2_R - 1
+static constexpr int Q2_ROWS = 112;         // buffer rows: the window slides through the buffer, no wrap-around
+static constexpr int Q2_PTOP = Q2_ROWS - 2 * Q2_HALF - 1;  // highest buffer row for the top of a window (43)
 
 struct Q2Args {
   double* Zt;     // kc x n (ld = ldzt)
@@ -349,90 +352,119 @@ struct Q2Args {
   const double* TAU;
   int maxhops;
   int* done;      // per hop index: lowest sweep already applied (INT_MAX initially)
+  long long* prof;  // optional (BK_Q2_PROF), CTA 0: [0] passes, [1] compute cycles, [2] barrier wait, [3] flag wait
 };
 
 // One CTA owns hop index t for all sweeps (j = jmax(t) .. 0).  The reflector (j, t) acts on rows
-// [j+1+64t, j+65+64t): the window slides up one row per sweep.  The window lives in a 128-row shared-memory
-// buffer (one column per compute thread) and slides towards row 0 of the buffer; when it gets there the
-// thread copies its 63 values back to the top (every ~64 sweeps), so every access uses a compile-time
-// offset from one moving base.  While the window is still growing (near the bottom of the matrix) and for
-// the last few sweeps a one-sweep-per-step path is used; in between every pass pulls the 63 resident rows
-// plus 4 new rows into registers, applies 4 consecutive reflectors and retires 4 rows, so that each window
-// element crosses shared memory once per 4 sweeps.  Rows retired by hop index t-1 are the rows entering the
-// window of hop index t: done[t-1] is the only synchronisation.
+// [j+1+64t, j+65+64t): the window slides up one row per sweep.  The window lives in a shared-memory buffer
+// (row lo of the current sweep at buffer row p, p decreasing; when p reaches the top the window is stored
+// back at the bottom, so every access is a compile-time offset from one moving base).
+//   fast path (full 64-row window): per pass the 63 resident rows plus 4 new rows go to registers, 4 consecutive
+//   reflectors are applied and 4 rows retire.  TWO threads share a column (rows 0..33 / 34..67 of the 68-row
+//   pass window, lanes l and l+16 of a warp): half the registers per thread, twice the warps to hide latency;
+//   both halves run the same instruction stream on zero-padded copies of the reflectors and combine their dot
+//   products with one shuffle.
+//   slow path (window still growing near the bottom of the matrix, last < 4 sweeps): one sweep per step from
+//   shared memory, one thread per column.
+// Rows retired by hop index t-1 are the rows entering the window of hop index t: done[t-1] is the only
+// synchronisation between CTAs (acquire/release, one warp of each CTA does nothing else).
 __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
   extern __shared__ __align__(16) double win[];  // Q2_ROWS x Q2_KC
-  __shared__ __align__(16) double vs[2][Q2_R][CB];
+  __shared__ __align__(16) double vsx[2][Q2_R][2][Q2_HALF];  // zero-padded reflectors of a pass, per half
   __shared__ double taus[2][Q2_R];
+  __shared__ double vs0[CB];  // slow path
+  __shared__ double tau0;
   const int n = a.n, kc = a.kc, tid = threadIdx.x;
-  const bool flagger = (tid == Q2_KC);  // lane 0 of the flag warp
-  const bool act = tid < kc;            // compute thread with a real column
-  const int nhop = (n - 3) / CB + 1;    // hop indices t with jmax(t) = n-3-t*CB >= 0
+  const bool flagger = (tid == Q2_CT);  // lane 0 of the flag warp
+  const bool comp = tid < Q2_CT;
+  const int col = comp ? ((tid >> 5) * 16 + (tid & 15)) : 0;
+  const int h = (tid >> 4) & 1;
+  const bool act = comp && col < kc;  // compute thread with a real column (global accesses)
+  const int nhop = (n - 3) / CB + 1;  // hop indices t with jmax(t) = n-3-t*CB >= 0
   const double* VV = a.VV;
-  double* col = win + (tid < Q2_KC ? tid : 0);  // this thread's column: row q at col[q * Q2_KC]
+  double* colp = win + col;  // this thread's column: buffer row q at colp[q * Q2_KC]
+  long long tk0 = 0;
+  if (a.prof) tk0 = clock64();
   for (int t = blockIdx.x; t < nhop; t += gridDim.x) {
     const int jmax = n - 3 - t * CB;
-    const int jfull = n - CB - 1 - t * CB;  // largest sweep whose window is a full 64 rows
     const int* pdone = a.done + t - 1;
     int* mydone = a.done + t;
     int j = jmax;
-    int p = CB;  // buffer row of the top row (lo) of the window of sweep j
-    // move the resident rows buf[p+1 .. p+cnt] to buf[CB+1 .. CB+cnt] (descending: the ranges may overlap)
-    auto rebase = [&](int cnt) {
-      if (act)
-        for (int i = cnt; i >= 1; --i) col[(CB + i) * Q2_KC] = col[(p + i) * Q2_KC];
-      p = CB;
+    int p = Q2_PTOP;  // buffer row of the top row (lo) of the window of sweep j
+    // rows past the end of the matrix (windows clipped at the bottom) are zero rows of the buffer
+    for (int i = tid; i < Q2_ROWS * Q2_KC; i += Q2_NT) win[i] = 0.0;
+    __syncthreads();
+    // move the resident rows buf[p+1 .. p+cnt] to buf[PTOP+1 .. PTOP+cnt] (descending: the ranges may overlap)
+    auto rebase_slow = [&](int cnt) {
+      if (comp && h == 0)
+        for (int i = cnt; i >= 1; --i) colp[(Q2_PTOP + i) * Q2_KC] = colp[(p + i) * Q2_KC];
+      p = Q2_PTOP;
     };
     // One sweep, window read from shared memory with run-time length (growing window / tail sweeps).
     auto slow_sweep = [&](int js, bool first) {
+      long long ts0 = 0;
+      if (a.prof) ts0 = clock64();
       const int lo = js + 1 + t * CB, hi = min(n, lo + CB), L = hi - lo;
-      if (p < 0) rebase(L - 1);
+      if (p < 0) rebase_slow(L - 1);
       if (t > 0 && flagger) {
         while (ld_acquire_i32(pdone) > js + 1) {
         }
       }
       __syncthreads();
-      if (act) {
+      if (act && h == 0) {
         if (first) {
-          for (int i = 0; i < L; ++i) col[(p + i) * Q2_KC] = __ldcg(a.Zt + tid + (size_t)(lo + i) * a.ldzt);
+          for (int i = 0; i < L; ++i) colp[(p + i) * Q2_KC] = __ldcg(a.Zt + col + (size_t)(lo + i) * a.ldzt);
         } else {
-          col[p * Q2_KC] = __ldcg(a.Zt + tid + (size_t)lo * a.ldzt);
+          colp[p * Q2_KC] = __ldcg(a.Zt + col + (size_t)lo * a.ldzt);
         }
       }
-      if (tid < L) vs[0][0][tid] = VV[(size_t)(lo + tid) + (size_t)js * n];
-      if (tid == 0) taus[0][0] = a.TAU[t + (size_t)js * a.maxhops];
+      if (tid < L) vs0[tid] = VV[(size_t)(lo + tid) + (size_t)js * n];
+      if (tid == 0) tau0 = a.TAU[t + (size_t)js * a.maxhops];
       __syncthreads();
-      if (act) {
+      if (act && h == 0) {
         double s0 = 0.0, s1 = 0.0;
         int i = 0;
         for (; i + 1 < L; i += 2) {
-          s0 = fma(vs[0][0][i], col[(p + i) * Q2_KC], s0);
-          s1 = fma(vs[0][0][i + 1], col[(p + i + 1) * Q2_KC], s1);
+          s0 = fma(vs0[i], colp[(p + i) * Q2_KC], s0);
+          s1 = fma(vs0[i + 1], colp[(p + i + 1) * Q2_KC], s1);
         }
-        if (i < L) s0 = fma(vs[0][0][i], col[(p + i) * Q2_KC], s0);
-        const double wv = taus[0][0] * (s0 + s1);
-        for (i = 0; i < L; ++i) col[(p + i) * Q2_KC] -= vs[0][0][i] * wv;
-        if (lo + CB <= n) a.Zt[tid + (size_t)(lo + CB - 1) * a.ldzt] = col[(p + CB - 1) * Q2_KC];
+        if (i < L) s0 = fma(vs0[i], colp[(p + i) * Q2_KC], s0);
+        const double wv = tau0 * (s0 + s1);
+        for (i = 0; i < L; ++i) colp[(p + i) * Q2_KC] -= vs0[i] * wv;
+        if (lo + CB <= n) a.Zt[col + (size_t)(lo + CB - 1) * a.ldzt] = colp[(p + CB - 1) * Q2_KC];
       }
       __syncthreads();
       if (flagger) st_release_i32(mydone, js);
       --p;
+      if (a.prof && blockIdx.x == 0 && tid == 0) {
+        a.prof[4] += 1;
+        a.prof[5] += clock64() - ts0;
+      }
     };
-    // ---- phase 1: the window grows from 2 to 63 rows ------------------------------------------------------
-    for (; j >= 0 && j > jfull; --j) slow_sweep(j, j == jmax);
-    // ---- phase 2: full window, Q2_R sweeps per pass ---------------------------------------------------------
-    if (j >= Q2_R - 1) {
-      // loads for a pass starting at sweep jp: its 4 new rows and its 4 reflectors
-      double pr[Q2_R], vreg = 0.0, treg = 0.0;
+    // ---- main phase: Q2_R sweeps per pass (windows clipped by the end of the matrix run on zero rows) ------
+    const bool fast_phase = (j >= Q2_R - 1);
+    if (fast_phase) {
+      // loads for a pass starting at sweep jp: its 4 new rows (two per half-thread) and its 4 reflectors
+      double pr[2], vreg = 0.0, treg = 0.0;
       auto issue_pass_loads = [&](int jp) {
         const int lo = jp + 1 + t * CB;
-#pragma unroll
-        for (int s = 0; s < Q2_R; ++s) pr[s] = act ? __ldcg(a.Zt + tid + (size_t)(lo - s) * a.ldzt) : 0.0;
-        if (tid < Q2_R * CB) {
-          const int s = tid >> 6, i = tid & (CB - 1);
-          vreg = VV[(size_t)(lo - s + i) + (size_t)(jp - s) * n];
+        pr[0] = act ? __ldcg(a.Zt + col + (size_t)(lo - 2 * h) * a.ldzt) : 0.0;
+        pr[1] = act ? __ldcg(a.Zt + col + (size_t)(lo - 2 * h - 1) * a.ldzt) : 0.0;
+        if (tid < Q2_R * 2 * Q2_HALF) {
+          // zero-padded reflector s on the pass window: window index i <-> row lo-3+i, reflector rows lo-s ..
+          const int s = tid / (2 * Q2_HALF), i = tid % (2 * Q2_HALF);
+          const int vi = i - (Q2_R - 1 - s);
+          vreg = (vi >= 0 && vi < CB && lo - s + vi < n) ? VV[(size_t)(lo - s + vi) + (size_t)(jp - s) * n] : 0.0;
         }
         if (tid < Q2_R) treg = a.TAU[t + (size_t)(jp - tid) * a.maxhops];
+      };
+      auto stage_pass = [&](int buf, int pn) {  // prefetched rows -> window buffer, reflectors -> vsx[buf]
+        if (comp) {
+          colp[(pn - 2 * h) * Q2_KC] = pr[0];
+          colp[(pn - 2 * h - 1) * Q2_KC] = pr[1];
+        }
+        if (tid < Q2_R * 2 * Q2_HALF) (&vsx[buf][0][0][0])[tid] = vreg;
+        if (tid < Q2_R) taus[buf][tid] = treg;
       };
       // a pass at sweep jp needs hop index t-1 to have applied sweep jp-2
       auto wait_pass = [&](int jp) {
@@ -444,78 +476,97 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
       wait_pass(j);
       if (j - Q2_R >= Q2_R - 1) wait_pass(j - Q2_R);
       __syncthreads();
+      {
+        // rows already below the top of the first window (the last rows of the matrix)
+        const int lo = j + 1 + t * CB;
+        if (act && h == 0)
+          for (int r = lo + 1; r < min(n, lo + CB); ++r)
+            colp[(p + r - lo) * Q2_KC] = __ldcg(a.Zt + col + (size_t)r * a.ldzt);
+      }
       issue_pass_loads(j);
       int cur = 0;
-      if (tid < Q2_R * CB) vs[cur][tid >> 6][tid & (CB - 1)] = vreg;
-      if (tid < Q2_R) taus[cur][tid] = treg;
-      double z[CB + Q2_R - 1];
-#pragma unroll
-      for (int s = 0; s < Q2_R; ++s) z[Q2_R - 1 - s] = pr[s];  // z[i] <-> row lo-3+i <-> buffer row p-3+i
+      stage_pass(cur, p);
       __syncthreads();
       while (j >= Q2_R - 1) {
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        if (a.prof) tq0 = clock64();
         const int lo = j + 1 + t * CB;
         const bool have_next = (j - Q2_R >= Q2_R - 1);
         if (have_next) issue_pass_loads(j - Q2_R);  // verified before the previous barrier
-        if (p < Q2_R - 1) rebase(CB - 1);
-        if (act) {
-          double* wb = col + (p - (Q2_R - 1)) * Q2_KC;
+        const int newp = (p - Q2_R >= 2 * Q2_R - 1) ? p - Q2_R : Q2_PTOP;
+        if (comp) {
+          // z[li] <-> pass-window index 34 h + li <-> row lo-3+34h+li <-> buffer row p-3+34h+li
+          const double* rb = colp + (p - (Q2_R - 1) + Q2_HALF * h) * Q2_KC;
+          double z[Q2_HALF];
 #pragma unroll
-          for (int i = Q2_R; i < CB + Q2_R - 1; ++i) z[i] = wb[i * Q2_KC];
+          for (int i = 0; i < Q2_HALF; ++i) z[i] = rb[i * Q2_KC];
+#pragma unroll 1
+          for (int s = 0; s < Q2_R; ++s) {  // the register indices do not depend on s: keep one copy of the body
+            const double2* v2p = reinterpret_cast<const double2*>(&vsx[cur][s][h][0]);
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-          for (int s = 0; s < Q2_R; ++s) {
-            const int off = Q2_R - 1 - s;
-            const double2* v2p = reinterpret_cast<const double2*>(&vs[cur][s][0]);
-            double sa[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int i = 0; i < CB; i += 4) {
-              const double2 va = v2p[i / 2], vb = v2p[i / 2 + 1];
-              const int q = i & 4;
-              sa[q] = fma(va.x, z[off + i], sa[q]);
-              sa[q + 1] = fma(va.y, z[off + i + 1], sa[q + 1]);
-              sa[q + 2] = fma(vb.x, z[off + i + 2], sa[q + 2]);
-              sa[q + 3] = fma(vb.y, z[off + i + 3], sa[q + 3]);
-            }
-            const double wv = taus[cur][s] * (((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7])));
-#pragma unroll
-            for (int i = 0; i < CB; i += 2) {
+            for (int i = 0; i < Q2_HALF; i += 2) {
               const double2 va = v2p[i / 2];
-              z[off + i] = fma(-va.x, wv, z[off + i]);
-              z[off + i + 1] = fma(-va.y, wv, z[off + i + 1]);
+              sa[i & 2] = fma(va.x, z[i], sa[i & 2]);
+              sa[(i & 2) + 1] = fma(va.y, z[i + 1], sa[(i & 2) + 1]);
+            }
+            double dot = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+            const double wv = taus[cur][s] * dot;
+#pragma unroll
+            for (int i = 0; i < Q2_HALF; i += 2) {
+              const double2 va = v2p[i / 2];
+              z[i] = fma(-va.x, wv, z[i]);
+              z[i + 1] = fma(-va.y, wv, z[i + 1]);
             }
           }
-          // retire the 4 bottom rows, keep the other 63 in the window
-          double* zt = a.Zt + tid + (size_t)(lo - (Q2_R - 1)) * a.ldzt;
+          // the 4 bottom rows (window indices 63..66 = local 29..32 of the lower half) retire
+          if (act && h == 1) {
+            double* zt = a.Zt + col + (size_t)(lo - (Q2_R - 1) + Q2_HALF) * a.ldzt;
 #pragma unroll
-          for (int i = CB - 1; i < CB + Q2_R - 1; ++i) zt[(size_t)i * a.ldzt] = z[i];
+            for (int i = CB - 1 - Q2_HALF; i < CB + Q2_R - 1 - Q2_HALF; ++i)
+              if (lo - (Q2_R - 1) + Q2_HALF + i < n) zt[(size_t)i * a.ldzt] = z[i];
+          }
+          // window index i goes to buffer row newp+1+i (row lo-3 becomes row lo'+1 of the next pass)
+          double* wb = colp + (newp + 1 + Q2_HALF * h) * Q2_KC;
 #pragma unroll
-          for (int i = 0; i < CB - 1; ++i) wb[i * Q2_KC] = z[i];
+          for (int i = 0; i < Q2_HALF; ++i) wb[i * Q2_KC] = z[i];
         }
-        p -= Q2_R;
+        p = newp;
         if (have_next) {
-          if (tid < Q2_R * CB) vs[cur ^ 1][tid >> 6][tid & (CB - 1)] = vreg;
-          if (tid < Q2_R) taus[cur ^ 1][tid] = treg;
-#pragma unroll
-          for (int s = 0; s < Q2_R; ++s) z[Q2_R - 1 - s] = pr[s];
+          stage_pass(cur ^ 1, p);
+          if (a.prof) tq1 = clock64();
           if (j - 2 * Q2_R >= Q2_R - 1) wait_pass(j - 2 * Q2_R);
         }
+        if (a.prof) tq2 = clock64();
         __syncthreads();
+        if (a.prof && blockIdx.x == 0) {
+          const long long tq3 = clock64();
+          if (tid == 0) {
+            a.prof[0] += 1;
+            a.prof[1] += tq2 - tq0;
+            a.prof[2] += tq3 - tq2;
+          }
+          if (flagger && have_next) a.prof[3] += tq2 - tq1;
+        }
         if (flagger) st_release_i32(mydone, j - (Q2_R - 1));
         cur ^= 1;
         j -= Q2_R;
       }
     }
-    // ---- phase 3: the last (< Q2_R) sweeps ----------------------------------------------------------------
-    for (; j >= 0; --j) slow_sweep(j, false);
+    // ---- the last (< Q2_R) sweeps, or every sweep of a hop index with fewer than Q2_R sweeps ------------------
+    for (; j >= 0; --j) slow_sweep(j, !fast_phase && j == jmax);
     // flush what is left of the window (nobody inside this kernel waits for these rows): after the last
     // sweep p points one above the row of lo0 = 1 + 64 t
     {
       const int lo0 = 1 + t * CB;
       const int cnt = ((lo0 + CB <= n) ? lo0 + CB - 1 : n) - lo0;
-      if (act)
-        for (int i = 0; i < cnt; ++i) a.Zt[tid + (size_t)(lo0 + i) * a.ldzt] = col[(p + 1 + i) * Q2_KC];
+      if (act && h == 0)
+        for (int i = 0; i < cnt; ++i) a.Zt[col + (size_t)(lo0 + i) * a.ldzt] = colp[(p + 1 + i) * Q2_KC];
     }
     __syncthreads();
   }
+  if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[6] = clock64() - tk0;
 }
 
 __global__ void transpose_kernel(const double* __restrict__ src, long long lds, int rows, int cols,
@@ -563,6 +614,13 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
     a.TAU = TAU;
     a.maxhops = maxhops;
     a.done = done.p;
+    DevBuf<long long> prof;
+    a.prof = nullptr;
+    if (getenv("BK_Q2_PROF")) {
+      BK_TRY(prof.alloc(8));
+      BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+      a.prof = prof.p;
+    }
     void* kargs[] = {&a};
     const int G = std::min(ctx->sm_count, nhop);
     BK_CUDA(cudaLaunchCooperativeKernel((void*)q2_apply_kernel, dim3(G), dim3(Q2_NT), kargs,
@@ -573,6 +631,15 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
     BK_LAUNCHED(ctx);
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (a.prof) {
+      long long h[8];
+      BK_CUDA(cudaMemcpyAsync(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+      const double np = (double)std::max(1LL, h[0]);
+      fprintf(stderr, "[q2 prof, CTA 0, kc=%d] passes %lld: cycles per pass: compute %.0f, barrier wait %.0f, flag wait %.0f; "
+              "slow sweeps %lld at %.0f cycles; CTA total %.3f Mcycles\n",
+              kc, h[0], h[1] / np, h[2] / np, h[3] / np, h[4], h[5] / (double)std::max(1LL, h[4]), h[6] * 1e-6);
+    }
   }
   return BK_OK;
 }
