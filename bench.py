@@ -295,6 +295,22 @@ def main():
     stage = {k: float(np.mean([i[k] for i in infos])) for k in
              ("t_kernel", "t_eigen", "t_tridiag", "t_sy2sb", "t_sb2st", "t_dc", "t_backtransform", "t_q2", "t_q1",
               "t_lambda", "t_coef", "t_vcov", "t_deriv", "t_total")}
+    # per-stage floors: algorithmic bytes / measured HBM peak, algorithmic flops / measured DMMA peak
+    hbm_peak, _ = measured_peaks()
+    rr = C.c_double()
+    check(lib.bk_microbench(ctx.handle, 1, 0, 0, C.byref(rr)))
+    dmma = float(rr.value) * 1e12
+    kk = float(info["lastkeeper"])
+    floors = {
+        "t_kernel": 8.0 * N * N / (hbm_peak * 1e9),
+        "t_eigen": ((4.0 / 3.0) * N ** 3 + 2.0 * N * N * kk) / dmma,
+        "t_lambda": info["n_passes"] * 8.0 * N * kk / (hbm_peak * 1e9),
+        "t_vcov": max(2.0 * N * N * kk / dmma, 2 * 8.0 * N * N / (hbm_peak * 1e9)),
+        "t_coef+t_deriv": 8.0 * N * N / (hbm_peak * 1e9),   # one pass over K: yhat, derivatives, variance vectors
+    }
+    stage["t_coef+t_deriv"] = stage["t_coef"] + stage["t_deriv"]
+    stage_roofline = {k: {"floor_s": v, "measured_s": stage[k], "frac": (v / stage[k]) if stage[k] > 0 else None}
+                      for k, v in floors.items()}
     line = {"metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -307,6 +323,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "stage_seconds": stage,
+            "stage_roofline": stage_roofline,
             "fit": {"lambda": info["lambda"], "lastkeeper": int(info["lastkeeper"]), "n_probes": info["n_probes"],
                     "n_passes": info["n_passes"], "dc_top_k": int(info["dc_top_k"])}}
     if world == 1 and not args.no_cpu_baseline:

@@ -64,15 +64,37 @@ long double ratio_sum(const std::vector<double>& ev, double x) {
 
 int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
   if (*U <= 0.0) {
-    double u = (double)n;
-    while ((double)ratio_sum(ev, u) < 1.0) {
-      u -= 1.0;
-      if (u <= 0.0) {
-        set_error("lambda search: upper bound loop did not terminate (degenerate spectrum)");
-        return BK_ERR_NUMERIC;
+    // Reference (R/bigKRLS_Rcpp_functions.R:16-20): U = n; while (sum(ev/(ev+U)) < 1) U = U - 1 - hundreds to
+    // thousands of O(Neig) sums.  f(U) = sum(ev/(ev+U)) is strictly decreasing with f(U) - f(U+1) ~ 1/U, many
+    // orders above the rounding of the sum, so the first integer step m with f(n-m) >= 1 is found by bisection
+    // and then checked against the scan's stopping rule (f(n-m) >= 1 and f(n-m+1) < 1); the sums themselves are
+    // evaluated exactly as before.
+    auto ok = [&](long long m) { return !((double)ratio_sum(ev, (double)n - (double)m) < 1.0); };
+    long long lo = 0, hi = -1;
+    if (ok(0)) {
+      hi = 0;
+    } else {
+      long long step = 1;
+      while (hi < 0) {  // gallop: lo is always a failing offset
+        const long long m = std::min<long long>(lo + step, (long long)n - 1);
+        if (ok(m)) {
+          hi = m;
+        } else {
+          lo = m;
+          if (m == (long long)n - 1) {
+            set_error("lambda search: upper bound loop did not terminate (degenerate spectrum)");
+            return BK_ERR_NUMERIC;
+          }
+          step *= 2;
+        }
       }
+      while (hi - lo > 1) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (ok(mid)) hi = mid; else lo = mid;
+      }
+      // lo fails, hi = lo + 1 passes: exactly where the linear scan stops
     }
-    *U = u;
+    *U = (double)n - (double)hi;
   }
   if (*L <= 0.0) {
     double l = 2.220446049250313e-16;  // .Machine$double.eps (R/bigKRLS_Rcpp_functions.R:28)

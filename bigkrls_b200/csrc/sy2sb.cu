@@ -140,12 +140,14 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
   }
 }
 
-// T (ib x ib upper triangular) from S = V'V and tau (same recurrence as ormtr.cu)
+// T (ib x ib upper triangular) from S = V'V and tau: T[:i,i] = -tau_i T[:i,:i] S[:i,i].  16 threads per row of T
+// share each dot product (the 64 steps are sequential; a single thread per row made a step cost a 64-long
+// dependent FMA chain).  Launch with 16 * ib threads.
 __global__ void sb_larft_kernel(const double* __restrict__ S, const double* __restrict__ tau, int ib,
                                 double* __restrict__ T) {
   extern __shared__ double ts[];  // T (ib x ib) then S (ib x ib)
   double* ss = ts + ib * ib;
-  const int r = threadIdx.x;
+  const int r = threadIdx.x >> 4, part = threadIdx.x & 15;
   for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) {
     ts[idx] = 0.0;
     ss[idx] = S[idx];
@@ -155,10 +157,16 @@ __global__ void sb_larft_kernel(const double* __restrict__ S, const double* __re
     const double ti = tau[i];
     double acc = 0.0;
     if (r < i)
-      for (int q = r; q < i; ++q) acc = fma(ts[r + q * ib], ss[q + i * ib], acc);
+      for (int q = r + part; q < i; q += 16) acc = fma(ts[r + q * ib], ss[q + i * ib], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     __syncthreads();
-    if (r < i) ts[r + i * ib] = -ti * acc;
-    if (r == i) ts[i + i * ib] = ti;
+    if (part == 0) {
+      if (r < i) ts[r + i * ib] = -ti * acc;
+      if (r == i) ts[i + i * ib] = ti;
+    }
     __syncthreads();
   }
   for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[idx];
@@ -244,7 +252,7 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     double* A22 = A + r0 + (long long)r0 * lda;
     double* Tk = Tstore + (size_t)k * b * b;
     BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vr, n, Vr, n, 0.0, S.p, b));
-    sb_larft_kernel<<<1, b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
+    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vr, n, Tk, b, 0.0, VT.p, m));               // V T
     mark();
