@@ -35,6 +35,7 @@ struct PanelArgs {
   double* part;     // [2][G][SB]
   double* prow;     // [2][SB]
   unsigned* barrier;
+  long long* prof;  // optional (BK_QR_PROF), CTA 0: cycles in [0] partial dots, [1] barrier, [2] reduction, [3] update, [4] columns
   int rows_per;
 };
 
@@ -57,21 +58,49 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
   __syncthreads();
 
   for (int j = 0; j < nr; ++j) {
+    long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+    if (a.prof) tc0 = clock64();
     const int buf = j & 1;
     double* part = a.part + (size_t)buf * G * SB;
     double* prow = a.prow + buf * SB;
     // ---- partial sums over own rows strictly below the pivot row j -----------------------------------
     const int rs = max(0, j + 1 - row_lo);  // first own local row with panel row > j
-    for (int l = j + warp; l < SB; l += QR_NT / 32) {
-      double s = 0.0;
-      for (int r = rs + lane; r < nrows; r += 32) s = fma(slab[r * LD + j], slab[r * LD + l], s);
-      s = warp_sum(s);
-      if (lane == 0) part[(size_t)blockIdx.x * SB + l] = s;
+    {
+      // warp w owns columns l = j + w + 8 q (q < 8): one pass over the rows accumulates all of them, then the
+      // eight warp reductions are interleaved (their shuffle latencies overlap)
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+      for (int r = rs + lane; r < nrows; r += 32) {
+        const double xj = slab[r * LD + j];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int l = j + warp + 8 * q;
+          if (l < SB) acc[q] = fma(xj, slab[r * LD + l], acc[q]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int l = j + warp + 8 * q;
+          if (l < SB) part[(size_t)blockIdx.x * SB + l] = acc[q];
+        }
+      }
     }
     if (j >= row_lo && j < row_lo + nrows) {
       for (int l = j + threadIdx.x; l < SB; l += QR_NT) prow[l] = slab[(j - row_lo) * LD + l];
     }
+    if (a.prof) {
+      __syncthreads();
+      tc1 = clock64();
+    }
     grid_barrier(a.barrier, epoch);
+    if (a.prof) tc2 = clock64();
     // ---- every CTA: totals, reflector, update coefficients ---------------------------------------------
     {
       // each CTA keeps its partials in one contiguous 512-byte row (a transposed layout with coalesced
@@ -79,15 +108,17 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
       const int l = j + (threadIdx.x >> 2), sub = threadIdx.x & 3;
       double s = 0.0;
       if (l < SB) {
-        // 8 loads in flight per thread, summed in a fixed order
-        for (int c0 = sub; c0 < G; c0 += 32) {
-          double v[8];
+        // all loads of a thread in flight at once (40 covers 160 CTAs per round), summed in a fixed order
+        for (int c0 = sub; c0 < G; c0 += 160) {
+          double v[40];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 40; ++q) {
             const int c = c0 + 4 * q;
             v[q] = (c < G) ? __ldcg(part + (size_t)c * SB + l) : 0.0;
           }
-          s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+#pragma unroll
+          for (int q = 0; q < 40; q += 8)
+            s += ((v[q] + v[q + 1]) + (v[q + 2] + v[q + 3])) + ((v[q + 4] + v[q + 5]) + (v[q + 6] + v[q + 7]));
         }
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -98,6 +129,7 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
       }
     }
     __syncthreads();
+    if (a.prof) tc3 = clock64();
     const double alpha = s_prow[j], xnorm2 = s_dots[j];
     double beta, tau, scale;
     if (xnorm2 == 0.0) {
@@ -111,10 +143,15 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.taus[j] = tau;
     // own rows below the pivot: P[r,l] -= v_r * t_l, then column j becomes v
-    for (int idx = threadIdx.x; idx < (nrows - rs) * (SB - j - 1); idx += QR_NT) {
-      const int r = rs + idx / (SB - j - 1), l = j + 1 + idx % (SB - j - 1);
-      const double tl = tau * (s_prow[l] + scale * s_dots[l]);
-      slab[r * LD + l] -= (scale * slab[r * LD + j]) * tl;
+    {
+      // thread = (column l, row phase): no integer division in the loop, consecutive lanes on consecutive columns
+      const int l = j + 1 + (threadIdx.x & (SB - 1)), rph = threadIdx.x >> 6;
+      if (l < SB) {
+        const double tl = tau * (s_prow[l] + scale * s_dots[l]);
+        const double stl = scale * tl;
+#pragma unroll 4
+        for (int r = rs + rph; r < nrows; r += QR_NT / SB) slab[r * LD + l] = fma(-slab[r * LD + j], stl, slab[r * LD + l]);
+      }
     }
     __syncthreads();
     for (int r = rs + threadIdx.x; r < nrows; r += QR_NT) slab[r * LD + j] *= scale;
@@ -124,6 +161,14 @@ __global__ void __launch_bounds__(QR_NT, 1) panel_qr_kernel(PanelArgs a) {
       if (threadIdx.x == 0) slab[(j - row_lo) * LD + j] = beta;
     }
     __syncthreads();
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+      const long long tc4 = clock64();
+      a.prof[0] += tc1 - tc0;
+      a.prof[1] += tc2 - tc1;
+      a.prof[2] += tc3 - tc2;
+      a.prof[3] += tc4 - tc3;
+      a.prof[4] += 1;
+    }
   }
   if (blockIdx.x == 0)
     for (int l = nr + threadIdx.x; l < SB; l += QR_NT) a.taus[l] = 0.0;
@@ -221,6 +266,11 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     cudaEventRecord(e, ctx->stream);
     ev.push_back(e);
   };
+  DevBuf<long long> prof;
+  if (getenv("BK_QR_PROF")) {
+    BK_TRY(prof.alloc(8));
+    BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+  }
   int k = 0;
   for (int c0 = 0; c0 < n; c0 += b, ++k) {
     const int r0 = c0 + b, m = n - r0;
@@ -240,6 +290,7 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     pa.part = part.p;
     pa.prow = prow.p;
     pa.barrier = ctx->barrier.p;
+    pa.prof = prof.p;
     const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(G, ceil_div(m, rows_target)));
     pa.rows_per = (int)ceil_div(m, Gp);
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
@@ -272,6 +323,14 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (prof.p) {
+    long long h[8];
+    BK_CUDA(cudaMemcpyAsync(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double nc = (double)std::max(1LL, h[4]);
+    fprintf(stderr, "[panel qr prof, CTA 0] columns %lld: cycles per column: partial dots %.0f, barrier %.0f, reduction %.0f, update %.0f\n",
+            h[4], h[0] / nc, h[1] / nc, h[2] / nc, h[3] / nc);
+  }
   if (stats) {
     double sec = 0.0;
     for (size_t i = 0; i + 1 < ev.size(); i += 2) {
