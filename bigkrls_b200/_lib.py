@@ -43,7 +43,7 @@ class FitOpts(C.Structure):
                 ("lambda_", C.c_double), ("L", C.c_double), ("U", C.c_double), ("tol", C.c_double),
                 ("derivative", C.c_int), ("vcov", C.c_int), ("n_which", C.c_int),
                 ("which", c_int32_p), ("y_sd", C.c_double), ("loo_batch", C.c_int),
-                ("keep_vcov_fitted", C.c_int)]
+                ("keep_vcov_fitted", C.c_int), ("K_host", C.c_void_p)]
 
 
 class FitInfo(C.Structure):

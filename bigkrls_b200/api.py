@@ -148,6 +148,14 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
         opts.which = wd0.ctypes.data_as(_lib.c_int32_p)
     h = C.c_void_p()
     cptr = C.byref(comm.struct) if comm is not None and comm.world > 1 else None
+    alloc = (lambda shape: ctx.pinned_empty(shape)) if pinned else (lambda shape: np.empty(shape, order="F"))
+    K = None
+    if return_squares:
+        # the kernel matrix is final after the first stage: hand its host buffer to the library so that the
+        # device->host copy runs under the eigensolver instead of after the fit
+        rank_, world_ = (comm.rank, comm.world) if cptr is not None else (0, 1)
+        K = alloc((n, n * (rank_ + 1) // world_ - n * rank_ // world_))
+        opts.K_host = K.ctypes.data
     check(lib.bk_fit_run(ctx.handle, dptr(Xs), dptr(ys), n, p, C.byref(opts), cptr, C.byref(h)))
     w._fit, w._ctx = h, ctx
     info = FitInfo()
@@ -165,7 +173,6 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
     yfit_std = np.empty(n)
     check(lib.bk_fit_get_yfitted(h, dptr(yfit_std)))
 
-    alloc = (lambda shape: ctx.pinned_empty(shape)) if pinned else (lambda shape: np.empty(shape, order="F"))
     c0, c1 = C.c_int64(), C.c_int64()
     check(lib.bk_fit_col_range(h, C.byref(c0), C.byref(c1)))
     w["_col_range"] = (c0.value, c1.value)
@@ -203,8 +210,8 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
     w["R2"] = float(1 - np.var(y0 - w["yfitted"], ddof=1) / y_sd ** 2)          # :430
     w["Looe"] = float(info.Le) * y_sd                                           # :431
     if return_squares:
-        K = alloc((n, ncols))
-        check(lib.bk_fit_get_K(h, dptr(K)))
+        assert K.shape == (n, ncols)
+        check(lib.bk_fit_get_K(h, dptr(K)))                                     # no-op: delivered during the fit
         w["K"] = K                                                              # :435
         if vcov_est:
             Vc = alloc((n, ncols))

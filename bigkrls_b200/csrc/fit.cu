@@ -41,6 +41,11 @@ struct bk_fit {
   bk_fit_info info;
   DevBuf<double> X, y, K, Q, ev, w, c, yhat, sig2, Vc, Vf, D, var, binfo;
   bool have_vcov = false, have_vf = false, have_deriv = false;
+  const double* K_host_done = nullptr;  // host buffer that already holds K (early D2H on the copy stream)
+  bool copy_pending = false;
+  ~bk_fit() {
+    if (copy_pending && ctx) cudaStreamSynchronize(ctx->copy_stream);  // K must outlive the queued copy
+  }
 };
 
 namespace {
@@ -262,6 +267,17 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     COMM_CALL(comm->allgatherv(comm->user, f->K.p, counts.data(), displs.data()), "allgatherv(K)");
   }
   f->info.t_kernel = tm.stop();
+  cudaEvent_t k_ready = nullptr;
+  if (o.K_host) {
+    // K is final: send this rank's column block to the host now, under the eigensolver
+    BK_CUDA(cudaEventCreateWithFlags(&k_ready, cudaEventDisableTiming));
+    BK_CUDA(cudaEventRecord(k_ready, ctx->stream));
+    BK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, k_ready, 0));
+    f->copy_pending = true;
+    BK_CUDA(cudaMemcpyAsync(o.K_host, f->K.p + (long long)f->c0 * ld, sizeof(double) * (size_t)n * (f->c1 - f->c0),
+                            cudaMemcpyDeviceToHost, ctx->copy_stream));
+    cudaEventDestroy(k_ready);
+  }
 
   // ---- 2/5 eigen ----------------------------------------------------------------------------
   tm.start();
@@ -510,6 +526,11 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   BK_CUDA(cudaMemcpyAsync(&f->sigmasq, f->sig2.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   f->info.t_deriv = tm.stop();
+  if (f->copy_pending) {
+    BK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    f->copy_pending = false;
+    f->K_host_done = o.K_host;
+  }
   f->info.t_total = total.stop();
 
   f->info.n = n;
@@ -627,6 +648,7 @@ void bk_fit_default_opts(bk_fit_opts* o, int64_t n, int64_t p) {
   o->y_sd = 1.0;
   o->loo_batch = 7;
   o->keep_vcov_fitted = 1;
+  o->K_host = nullptr;
 }
 
 int bk_fit_run(bk_ctx* ctx, const double* Xs, const double* ys, int64_t n, int64_t p,
@@ -656,6 +678,7 @@ int bk_fit_col_range(const bk_fit* f, int64_t* c0, int64_t* c1) {
 }
 int bk_fit_get_K(const bk_fit* f, double* host) {
   BK_REQUIRE(f && host, "bk_fit_get_K: NULL argument");
+  if (host == f->K_host_done) return BK_OK;  // delivered during the fit (bk_fit_opts.K_host)
   return get_vec(f, f->K.p + (long long)f->c0 * f->n, (size_t)f->n * (size_t)(f->c1 - f->c0), host);
 }
 int bk_fit_get_eigenvalues(const bk_fit* f, double* host) {

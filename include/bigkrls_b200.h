@@ -154,6 +154,10 @@ typedef struct bk_fit_opts {
   double y_sd;             /* sd(y) of the un-standardised y: folded into vcov outputs (R/bigKRLS.R:439,446) */
   int loo_batch;           /* lambda candidates evaluated per pass over Q (speculative tree), 1..15; 0 = default 7 */
   int keep_vcov_fitted;    /* 0: skip vcov.fitted (e.g. folds of a cross-validation) */
+  double* K_host;          /* optional HOST destination for this rank's column block of K (n x (c1-c0), c0 = n*rank/world,
+                              c1 = n*(rank+1)/world): the copy is queued on a second stream as soon as the kernel stage
+                              is done and overlaps the eigensolver; complete when bk_fit_run returns (pinned memory
+                              recommended).  bk_fit_get_K with the same pointer is then a no-op. */
 } bk_fit_opts;
 
 BK_API void bk_fit_default_opts(bk_fit_opts* o, int64_t n, int64_t p);
