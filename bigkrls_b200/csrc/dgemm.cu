@@ -19,6 +19,7 @@
 // Variants: transposed operands, batched (array of problem descriptors, blockIdx.z),
 // lower-triangle-only tile skipping (SYRK/SYR2K-like updates), deterministic split-K for
 // short-and-wide reductions (partials to a workspace, fixed-order reduce).
+#include <cmath>
 #include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -379,11 +380,27 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
     }
   }
   const int tiles = (int)(ceil_div(m, bm) * ceil_div(n, bn));
-  // deterministic split-K when the tile grid cannot fill the machine and k is long
+  // deterministic split-K when the tile grid cannot fill the machine and k is long.  The number of splits is
+  // chosen against wave quantisation: tiles * splits CTAs run in waves of (resident CTAs per SM) * SMs, and a
+  // last wave that is 10 % full costs as much as a full one (e.g. 157 tiles x 4 splits on 296 slots = 2.12 waves).
   int splits = 1;
-  if (!lower && tiles < 2 * ctx->sm_count && k >= 1024) {
-    splits = (int)std::min<int64_t>(ceil_div(4 * ctx->sm_count, tiles), k / 256);
-    splits = std::max(1, std::min(splits, 64));
+  const int resident = (bm == 128 && bn == 128) ? 1 : (bm == 64 ? 3 : 2);
+  const int slots = resident * ctx->sm_count;
+  if (!lower && tiles < 2 * slots && k >= 1024) {
+    const int smax = (int)std::max<int64_t>(1, std::min<int64_t>(64, k / 256));
+    if ((long long)tiles * smax <= slots) {
+      splits = smax;  // cannot even fill one wave: as many splits as the k extent allows
+    } else {
+      double best = -1.0;
+      for (int sct = 1; sct <= smax; ++sct) {
+        const double waves = (double)tiles * sct / slots;
+        const double score = waves / std::ceil(waves) - 0.004 * sct;  // small penalty: partials are extra traffic
+        if (score > best) {
+          best = score;
+          splits = sct;
+        }
+      }
+    }
   }
   double* ws = nullptr;
   if (splits > 1) {
