@@ -15,6 +15,7 @@
 // retires one finished row per sweep.  CTA t consumes the rows retired by CTA t-1 (flag per hop index), so the
 // whole back-transformation is a software pipeline over hop indices with no grid barrier.
 #include <climits>
+#include <type_traits>
 #include <cstdlib>
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -63,6 +64,26 @@ __device__ __forceinline__ void house_scalars(double alpha, double s, double& be
   }
 }
 
+// Group B's balanced, coalesced map of the lower triangle of a 64 x 64 block onto 128 threads x 17 slots: columns p
+// and 63-p hold 65 elements together; warp w takes the pairs p = w, w+4, ..., w+28, slots 0..63 of a pair go to
+// lanes (two rounds), slot 64 (row 63 of column 63-p) to lane (p - w)/4 in round 16.  Returns false for an empty slot.
+__device__ __forceinline__ bool tri_slot(int q, int gw, int lane, int& row, int& col) {
+  if (q < 16) {
+    const int p = gw + 4 * (q >> 1), slot = lane + 32 * (q & 1);
+    if (slot < CB - p) {
+      col = p;
+      row = p + slot;
+    } else {
+      col = CB - 1 - p;
+      row = slot - 1;  // (63 - p) + (slot - (64 - p))
+    }
+    return true;
+  }
+  col = CB - 1 - (gw + 4 * lane);
+  row = CB - 1;
+  return lane < 8;
+}
+
 // The CTA is split into two groups of 128 threads that work concurrently inside a hop: group A owns the
 // reflector chain (block below the diagonal block: right-update, new reflector, left-update), group B the
 // two-sided update of the diagonal block.  Both hold their 64 x 64 block in registers (32 doubles per
@@ -71,7 +92,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
   extern __shared__ __align__(16) double chase_sm[];
   double (*Ds)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chase_sm);
   double (*Bs)[CB + 1] = Ds + CB;
-  __shared__ double v[CB], v2[CB], w[CB], wa[CB];
+  __shared__ double v[CB], v2[CB], w[CB], w2[CB], wa[CB];
   __shared__ double pA[2][CB], pD[2][CB], redA[4], redB[4];
   __shared__ double s_alpha, s_tau0, s_tau2;
   const int n = a.n;
@@ -88,6 +109,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       if (t == 0 && L < 2) break;
       const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
       long long tp0 = 0, tp1 = 0;
+      long long tpa[6] = {0, 0, 0, 0, 0, 0};
       if (a.prof) tp0 = clock64();
       // ---- wait until sweep j-1 is two hops ahead (also orders the v <- v2 copy of the previous hop) -------
       if (j > 0 && tid == 0) {
@@ -96,164 +118,181 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       }
       __syncthreads();
       if (a.prof) tp1 = clock64();
-      // ---- every global load of the hop is issued up front ------------------------------------------------
-      double x[32];
-      double colv = 0.0;
-      if (grp == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = cq + 2 * i;
-          const int dd = L + r - c;  // row hi+r, column lo+c
-          x[i] = (r < L2 && c < L && dd < LDAB) ? __ldcg(AB + dd + (size_t)(lo + c) * LDAB) : 0.0;
-        }
-        if (t == 0 && gt < L) colv = __ldcg(AB + (1 + gt) + (size_t)j * LDAB);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = cq + 2 * i;
-          x[i] = (r >= c && r < L) ? __ldcg(AB + (r - c) + (size_t)(lo + c) * LDAB) : 0.0;
-        }
-      }
-      if (t == 0) {
-        // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
-        if (grp == 0) {
-          double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
-          s = warp_sum(s);
-          if (lane == 0) redA[gw] = s;
-          if (gt == 0) s_alpha = colv;
-          group_bar(1);
-          double beta, tau0, scale;
-          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
-          if (gt < L) v[gt] = (gt == 0) ? 1.0 : colv * scale;
-          if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
-          if (gt == 0) {
-            AB[1 + (size_t)j * LDAB] = beta;
-            a.e[j] = beta;
-            a.d[j] = __ldcg(AB + (size_t)j * LDAB);
-            s_tau0 = tau0;
-          }
-        }
-        __syncthreads();
-        tau = s_tau0;
-      }
       const bool has_b = hi < n;
       const bool more = has_b && (L2 >= 2);
-      if (grp == 1) {
-        // ================= group B: two-sided update of D = A[lo:hi, lo:hi] =================================
-        if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
-        if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = cq + 2 * i;
-          if (r >= c && r < L) {
-            Ds[r][c] = x[i];
-            Ds[c][r] = x[i];
-          }
-        }
-        group_bar(2);
-        {
-          // w = tau D v: half of the columns per thread, row r
-          double sa[4] = {0.0, 0.0, 0.0, 0.0};
-          if (r < L) {
-            const int c0 = cq * 32;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (c0 + c < L) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
-          }
-          pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-        }
-        group_bar(2);
-        {
-          const double wr0 = (gt < L) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
-          if (gt < CB) w[gt] = wr0;
-          double s = (gt < L) ? wr0 * v[gt] : 0.0;
-          s = warp_sum(s);
-          if (lane == 0) redB[gw] = s;
-        }
-        group_bar(2);
-        {
-          const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
-          const double vr = (r < L) ? v[r] : 0.0;
-          const double wr = (r < L) ? fma(al, vr, w[r]) : 0.0;
-#pragma unroll
+      const int Lrt = L, L2rt = L2;
+      // The hop body is instantiated twice: FULL (64 x 64 blocks, the common case) has no bounds predicates and
+      // constant address strides; the generic version handles the clipped blocks at the end of the band.
+      auto hop = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int L = FULL ? CB : Lrt, L2 = FULL ? CB : L2rt;
+        double* const pb = AB + (size_t)lo * LDAB + (L + r);  // block below the diagonal block, row hi + r
+        double* const pd0 = AB + (size_t)lo * LDAB;           // diagonal block: (row, col) at pd0[row + col (LDAB-1)]
+        // ---- every global load of the hop is issued up front ------------------------------------------------
+        double x[32];
+        double colv = 0.0;
+        if (grp == 0) {
+  #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int c = cq + 2 * i;
-            if (r >= c && r < L) {
-              const double vc = v[c], wc = fma(al, vc, w[c]);
-              AB[(r - c) + (size_t)(lo + c) * LDAB] = x[i] - vr * wc - wr * vc;
+            const int dd = L + r - c;  // row hi+r, column lo+c: AB[dd + (lo+c) LDAB] = pb[c (LDAB-1)]
+            x[i] = (FULL || (r < L2 && c < L && dd < LDAB)) ? __ldcg(pb + c * (LDAB - 1)) : 0.0;
+          }
+          if (t == 0 && gt < L) colv = __ldcg(AB + (1 + gt) + (size_t)j * LDAB);
+        } else {
+  #pragma unroll
+          for (int q = 0; q < 17; ++q) {
+            int row, col;
+            const bool ok = tri_slot(q, gw, lane, row, col) && (FULL || row < L);
+            x[q] = ok ? __ldcg(pd0 + row + col * (LDAB - 1)) : 0.0;  // AB[(row-col) + (lo+col) LDAB]
+          }
+        }
+        if (t == 0) {
+          // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
+          if (grp == 0) {
+            double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redA[gw] = s;
+            if (gt == 0) s_alpha = colv;
+            group_bar(1);
+            double beta, tau0, scale;
+            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
+            if (gt < L) v[gt] = (gt == 0) ? 1.0 : colv * scale;
+            if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
+            if (gt == 0) {
+              AB[1 + (size_t)j * LDAB] = beta;
+              a.e[j] = beta;
+              a.d[j] = __ldcg(AB + (size_t)j * LDAB);
+              s_tau0 = tau0;
             }
           }
+          __syncthreads();
+          tau = s_tau0;
         }
-      } else if (has_b) {
-        // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
-        {
-          double sa[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = cq + 2 * i;
-            if (c < L) sa[i & 3] = fma(x[i], v[c], sa[i & 3]);
+        if (grp == 1) {
+          // ================= group B: two-sided update of D = A[lo:hi, lo:hi] =================================
+          if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
+          if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
+  #pragma unroll
+          for (int q = 0; q < 17; ++q) {
+            int row, col;
+            if (tri_slot(q, gw, lane, row, col) && (FULL || row < L)) {
+              Ds[row][col] = x[q];
+              Ds[col][row] = x[q];
+            }
           }
-          pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-        }
-        group_bar(1);
-        {
-          const double ur = tau * (pA[0][r] + pA[1][r]);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = cq + 2 * i;
-            if (c < L) x[i] = fma(-ur, v[c], x[i]);
-          }
-        }
-        if (more) {
-          // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
-          double s = (cq == 0 && r >= 1 && r < L2) ? x[0] * x[0] : 0.0;
-          s = warp_sum(s);
-          if (lane == 0) redA[gw] = s;
-          if (gt == 0) s_alpha = x[0];
-          group_bar(1);
-          double beta, tau2, scale;
-          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
-          if (cq == 0) {
-            if (r < L2) v2[r] = (r == 0) ? 1.0 : x[0] * scale;
-            x[0] = (r == 0) ? beta : 0.0;
-          }
-          if (gt == 0) s_tau2 = tau2;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = cq + 2 * i;
-            if (r < L2 && c < L) Bs[r][c] = x[i];
-          }
-          group_bar(1);
+          group_bar(2);
           {
-            // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
+            // w = tau D v: half of the columns per thread, row r
             double sa[4] = {0.0, 0.0, 0.0, 0.0};
             if (r < L) {
-              const int q0 = cq * 32;
-#pragma unroll
-              for (int q = 0; q < 32; ++q)
-                if (q0 + q < L2) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
+              const int c0 = cq * 32;
+  #pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (c0 + c < L) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
+            }
+            pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+          }
+          group_bar(2);
+          {
+            const double wr0 = (gt < L) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
+            if (gt < CB) w[gt] = wr0;
+            double s = (gt < L) ? wr0 * v[gt] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redB[gw] = s;
+          }
+          group_bar(2);
+          {
+            const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
+            if (gt < CB) w2[gt] = (gt < L) ? fma(al, v[gt], w[gt]) : 0.0;  // w + al v
+            group_bar(2);
+  #pragma unroll
+            for (int q = 0; q < 17; ++q) {
+              int row, col;
+              if (tri_slot(q, gw, lane, row, col) && (FULL || row < L))
+                pd0[row + col * (LDAB - 1)] = x[q] - v[row] * w2[col] - w2[row] * v[col];
+            }
+          }
+        } else if (has_b) {
+          // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
+          {
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              if (c < L) sa[i & 3] = fma(x[i], v[c], sa[i & 3]);
             }
             pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
           }
           group_bar(1);
-          if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
-          group_bar(1);
+          if (a.prof && tid == 0) tpa[1] = clock64();
           {
-            const double v2r = (r < L2) ? v2[r] : 0.0;
-#pragma unroll
+            const double ur = tau * (pA[0][r] + pA[1][r]);
+  #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int c = cq + 2 * i;
-              if (c >= 1 && c < L) x[i] = fma(-v2r, wa[c], x[i]);
+              if (c < L) x[i] = fma(-ur, v[c], x[i]);
             }
           }
+          if (more) {
+            // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
+            double s = (cq == 0 && r >= 1 && r < L2) ? x[0] * x[0] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redA[gw] = s;
+            if (gt == 0) s_alpha = x[0];
+            group_bar(1);
+            if (a.prof && tid == 0) tpa[2] = clock64();
+            double beta, tau2, scale;
+            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
+            if (cq == 0) {
+              if (r < L2) v2[r] = (r == 0) ? 1.0 : x[0] * scale;
+              x[0] = (r == 0) ? beta : 0.0;
+            }
+            if (gt == 0) s_tau2 = tau2;
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              if (r < L2 && c < L) Bs[r][c] = x[i];
+            }
+            group_bar(1);
+            if (a.prof && tid == 0) tpa[3] = clock64();
+            {
+              // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
+              double sa[4] = {0.0, 0.0, 0.0, 0.0};
+              if (r < L) {
+                const int q0 = cq * 32;
+  #pragma unroll
+                for (int q = 0; q < 32; ++q)
+                  if (q0 + q < L2) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
+              }
+              pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+            }
+            group_bar(1);
+            if (a.prof && tid == 0) tpa[4] = clock64();
+            if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
+            group_bar(1);
+            if (a.prof && tid == 0) tpa[5] = clock64();
+            {
+              const double v2r = (r < L2) ? v2[r] : 0.0;
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = cq + 2 * i;
+                if (c >= 1 && c < L) x[i] = fma(-v2r, wa[c], x[i]);
+              }
+            }
+          }
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            const int dd = L + r - c;
+            if (FULL || (r < L2 && c < L && dd < LDAB)) pb[c * (LDAB - 1)] = x[i];
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = cq + 2 * i;
-          const int dd = L + r - c;
-          if (r < L2 && c < L && dd < LDAB) AB[dd + (size_t)(lo + c) * LDAB] = x[i];
-        }
-      }
+      };
+      if (L == CB && has_b && L2 == CB)
+        hop(std::true_type{});
+      else
+        hop(std::false_type{});
       long long tp2 = 0;
       if (a.prof) tp2 = clock64();
       __syncthreads();
@@ -264,6 +303,14 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
           a.prof[1] += tp1 - tp0;
           a.prof[2] += tp2 - tp1;
           a.prof[4] += tp3 - tp0;
+          if (tpa[5] != 0) {  // a hop with a full group-A chain
+            a.prof[5] += 1;
+            a.prof[6] += tpa[1] - tp1;     // loads + mat-vec partials
+            a.prof[7] += tpa[2] - tpa[1];  // rank-1 + norm
+            a.prof[8] += tpa[3] - tpa[2];  // scalars + staging
+            a.prof[9] += tpa[5] - tpa[3];  // column dots
+            a.prof[10] += tp2 - tpa[5];    // apply + stores
+          }
         } else {
           a.prof[3] += tp2 - tp1;
         }
@@ -306,8 +353,8 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   DevBuf<long long> prof;
   a.prof = nullptr;
   if (getenv("BK_CHASE_PROF")) {
-    BK_TRY(prof.alloc(8));
-    BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
+    BK_TRY(prof.alloc(16));
+    BK_CUDA(cudaMemsetAsync(prof.p, 0, 16 * sizeof(long long), ctx->stream));
     a.prof = prof.p;
   }
   if (n > 2) {
@@ -323,12 +370,13 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   BK_CUDA(cudaGetLastError());
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (a.prof) {
-    long long h[8];
+    long long h[16];
     BK_CUDA(cudaMemcpyAsync(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    const double hops = (double)std::max(1LL, h[0]);
-    fprintf(stderr, "[chase prof, CTA 0] hops %lld: cycles per hop: wait %.0f, group A %.0f, group B %.0f, total %.0f\n",
-            h[0], h[1] / hops, h[2] / hops, h[3] / hops, h[4] / hops);
+    const double hops = (double)std::max(1LL, h[0]), fa = (double)std::max(1LL, h[5]);
+    fprintf(stderr, "[chase prof, CTA 0] hops %lld: cycles per hop: wait %.0f, group A %.0f, group B %.0f, total %.0f | "
+            "group A chain: loads+matvec %.0f, rank-1+norm %.0f, scalars+staging %.0f, column dots %.0f, apply+stores %.0f\n",
+            h[0], h[1] / hops, h[2] / hops, h[3] / hops, h[4] / hops, h[6] / fa, h[7] / fa, h[8] / fa, h[9] / fa, h[10] / fa);
   }
   return BK_OK;
 }
