@@ -304,22 +304,34 @@ __global__ void dc_copy_defl_kernel(const MergeDesc* __restrict__ descs, const d
   }
 }
 
-// ---- secular equation: one thread per root ---------------------------------------------------
+// ---- secular equation: DC_LPR lanes per root (the poles are split over the lanes, butterfly sums give every
+// lane the same bits, so the lanes of a root take identical decisions) ------------------------------------------
+static constexpr int DC_LPR = 8;
+__device__ __forceinline__ double lpr_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = 1; o < DC_LPR; o <<= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
 __global__ void dc_secular_kernel(const MergeDesc* __restrict__ descs, const double* __restrict__ dlam,
                                   const double* __restrict__ w, int* __restrict__ org,
                                   double* __restrict__ mu, double* __restrict__ Dnew,
                                   int* __restrict__ fail) {
   const MergeDesc m = descs[blockIdx.y];
   const int K = m.K;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= K) return;
+  const int jraw = (blockIdx.x * blockDim.x + threadIdx.x) / DC_LPR, sub = threadIdx.x % DC_LPR;
+  if (K <= 0) return;
+  const unsigned gmask = ((1u << DC_LPR) - 1u) << ((threadIdx.x & 31) & ~(DC_LPR - 1));  // the lanes of this root
+  const bool active = jraw < K;            // inactive lane groups keep shuffling along with a clamped root
+  const int j = active ? jraw : K - 1;
   const double* dl = dlam + m.lo;
   const double* ww = w + m.lo;
   const double rho = m.rho;
   if (K == 1) {
-    org[m.lo] = 0;
-    mu[m.lo] = rho * ww[0] * ww[0];
-    Dnew[m.lo] = dl[0] + mu[m.lo];
+    if (active && sub == 0) {
+      org[m.lo] = 0;
+      mu[m.lo] = rho * ww[0] * ww[0];
+      Dnew[m.lo] = dl[0] + mu[m.lo];
+    }
     return;
   }
   const bool last = (j == K - 1);
@@ -328,14 +340,16 @@ __global__ void dc_secular_kernel(const MergeDesc* __restrict__ descs, const dou
   if (last) {
     o = K - 1;
     double s = 0.0;
-    for (int i = 0; i < K; ++i) s += ww[i] * ww[i];
+    for (int i = sub; i < K; i += DC_LPR) s += ww[i] * ww[i];
+    s = lpr_sum(s, gmask);
     lo = 0.0;
     hi = rho * s;
   } else {
     const double dj = dl[j];
     const double half = 0.5 * (dl[j + 1] - dj);
     double s = 0.0;
-    for (int i = 0; i < K; ++i) s += ww[i] * ww[i] / ((dl[i] - dj) - half);
+    for (int i = sub; i < K; i += DC_LPR) s += ww[i] * ww[i] / ((dl[i] - dj) - half);
+    s = lpr_sum(s, gmask);
     const double gmid = 1.0 + rho * s;
     if (gmid >= 0.0) {
       o = j;
@@ -354,18 +368,22 @@ __global__ void dc_secular_kernel(const MergeDesc* __restrict__ descs, const dou
   bool converged = false;
   for (int it = 0; it < 120; ++it) {
     double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0;
-    for (int i = 0; i <= j; ++i) {
+    for (int i = sub; i <= j; i += DC_LPR) {
       const double inv = 1.0 / ((dl[i] - dorg) - x);
       const double t = ww[i] * ww[i] * inv;
       psi += t;
       dpsi = fma(t, inv, dpsi);
     }
-    for (int i = j + 1; i < K; ++i) {
+    for (int i = j + 1 + sub; i < K; i += DC_LPR) {
       const double inv = 1.0 / ((dl[i] - dorg) - x);
       const double t = ww[i] * ww[i] * inv;
       phi += t;
       dphi = fma(t, inv, dphi);
     }
+    psi = lpr_sum(psi, gmask);
+    phi = lpr_sum(phi, gmask);
+    dpsi = lpr_sum(dpsi, gmask);
+    dphi = lpr_sum(dphi, gmask);
     psi *= rho;
     phi *= rho;
     dpsi *= rho;
@@ -415,10 +433,12 @@ __global__ void dc_secular_kernel(const MergeDesc* __restrict__ descs, const dou
     if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);  // also catches NaN / inf
     x = nx;
   }
-  if (!converged) atomicExch(fail, 2);
-  org[m.lo + j] = o;
-  mu[m.lo + j] = x;
-  Dnew[m.lo + j] = dorg + x;
+  if (active && sub == 0) {
+    if (!converged) atomicExch(fail, 2);
+    org[m.lo + j] = o;
+    mu[m.lo + j] = x;
+    Dnew[m.lo + j] = dorg + x;
+  }
 }
 
 __device__ __forceinline__ double dc_delta(const double* dl, const int* org, const double* mu, int i,
@@ -705,7 +725,7 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
       BK_LAUNCHED(ctx);
     }
     if (maxK > 0) {
-      dc_secular_kernel<<<dim3((unsigned)ceil_div(maxK, 128), nm), 128, 0, ctx->stream>>>(
+      dc_secular_kernel<<<dim3((unsigned)ceil_div((long long)maxK * DC_LPR, 128), nm), 128, 0, ctx->stream>>>(
           desc_d.p, dlam_d.p, w_d.p, org_d.p, mu_d.p, Dnew.p, fail_d.p);
       BK_LAUNCHED(ctx);
       if (h == height && nm == 1) {
