@@ -132,6 +132,7 @@ RcppExport SEXP _bigKRLS_fit(SEXP pXs, SEXP ys, SEXP sigma, SEXP Neig, SEXP eigt
   o.n_which = (int)w0.size();
   o.which = w0.empty() ? nullptr : w0.data();
   o.y_sd = as<double>(ysd);
+  if (!Rf_isNull(pK)) o.K_host = mat(pK);  // copied under the eigensolver; bk_fit_get_K below is then a no-op
   bk_fit* f = nullptr;
   chk(bk_fit_run(ctx(), mat(pXs), y.begin(), n, p, &o, nullptr, &f));
   bk_fit_info info;
