@@ -71,3 +71,22 @@ def test_twostage_matches_onestage_fit(ctx, monkeypatch):
     assert abs(out["0"][0] - out["1"][0]) <= 1e-9 * abs(out["0"][0])
     assert np.max(np.abs(out["0"][1] - out["1"][1])) <= 1e-8 * np.max(np.abs(out["0"][1]))
     assert np.max(np.abs(out["0"][2] - out["1"][2])) <= 1e-8 * np.max(np.abs(out["0"][2]))
+
+
+def test_wide_spectrum_falls_back_to_onestage(ctx, monkeypatch):
+    """With an eigenvalue threshold the solver starts two-stage; when the threshold keeps more than n/3
+    eigenvectors (flat spectrum: many dimensions) it must fall back to the one-stage path and give exactly
+    the one-stage result."""
+    from bigkrls_b200 import api
+    X, y = o.synthetic(4200, 40, 3)
+    monkeypatch.delenv("BK_EIG_TWOSTAGE", raising=False)
+    fit = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False)
+    assert fit["lastkeeper"] > 4200 // 3
+    assert fit["_info"]["twostage"] == 0.0
+    ref_c, ref_lam = np.array(fit["coeffs"]).copy(), fit["lambda"]
+    fit.release_device()
+    monkeypatch.setenv("BK_EIG_TWOSTAGE", "0")
+    fit0 = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False)
+    assert fit0["lambda"] == ref_lam
+    assert np.array_equal(np.array(fit0["coeffs"]), ref_c)
+    fit0.release_device()
