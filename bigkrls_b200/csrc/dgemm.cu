@@ -386,7 +386,7 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
   int splits = 1;
   const int resident = (bm == 128 && bn == 128) ? 1 : (bm == 64 ? 3 : 2);
   const int slots = resident * ctx->sm_count;
-  if (!lower && tiles < 2 * slots && k >= 1024) {
+  if (!lower && tiles < 8 * slots && k >= 1024) {
     const int smax = (int)std::max<int64_t>(1, std::min<int64_t>(64, k / 256));
     if ((long long)tiles * smax <= slots) {
       splits = smax;  // cannot even fill one wave: as many splits as the k extent allows
