@@ -198,23 +198,26 @@ __global__ void sb_larft_kernel(const double* __restrict__ S, const double* __re
     ss[idx] = S[idx];
   }
   __syncthreads();
+  __shared__ double s_tau[64];
+  if (threadIdx.x < ib) s_tau[threadIdx.x] = tau[threadIdx.x];
+  __syncthreads();
   for (int i = 0; i < ib; ++i) {
-    const double ti = tau[i];
+    const double ti = s_tau[i];
     double acc = 0.0;
     if (r < i)
-      for (int q = r + part; q < i; q += 16) acc = fma(ts[r + q * ib], ss[q + i * ib], acc);
+      for (int q = r + part; q < i; q += 16) acc = fma(ts[r * ib + q], ss[q + i * ib], acc);  // ts holds T row-major
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     __syncthreads();
     if (part == 0) {
-      if (r < i) ts[r + i * ib] = -ti * acc;
-      if (r == i) ts[i + i * ib] = ti;
+      if (r < i) ts[r * ib + i] = -ti * acc;
+      if (r == i) ts[i * ib + i] = ti;
     }
     __syncthreads();
   }
-  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[idx];
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[(idx % ib) * ib + idx / ib];
 }
 
 // AB[d + j*ldab] = A[j+d, j] for d <= b, 0 for b < d < ldab   (lower band, working width 2b)
