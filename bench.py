@@ -322,6 +322,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "per_step_seconds": [float(i["t_total"]) for i in infos],
             "stage_seconds": stage,
             "stage_roofline": stage_roofline,
             "fit": {"lambda": info["lambda"], "lastkeeper": int(info["lastkeeper"]), "n_probes": info["n_probes"],

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "bk_destroy": (None, [C.c_void_p]),
     "bk_device_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), c_int64_p, c_int64_p]),
     "bk_launch_count": (C.c_int64, [C.c_void_p]),
+    "bk_trim": (C.c_int, [C.c_void_p]),
     "bk_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "bk_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bk_gauss_kernel": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, C.c_double, c_double_p]),
@@ -195,6 +196,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def trim(self):
+        """Give cached device memory back (eigensolver work matrices kept between fits, unused pool blocks)."""
+        check(self._lib.bk_trim(self.handle))
 
     def device_info(self):
         name = C.create_string_buffer(256)

@@ -62,6 +62,12 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
+    if (p && borrowed) {
+      p = nullptr;
+      n = 0;
+      borrowed = false;
+      return;
+    }
     if (p) {
       // stream-ordered free: the block returns to the pool once the work queued so far has used it
       if (!pooled || cudaFreeAsync(p, pool_stream) != cudaSuccess) {
@@ -99,6 +105,19 @@ struct DevBuf {
     if (count <= n && p) return BK_OK;
     return alloc(count);
   }
+  // Use (a prefix of) a long-lived cache buffer instead of an allocation of one's own: the cache grows if it has
+  // to and is never freed by this object.  For the multi-GB transient work matrices of the eigensolver, whose
+  // allocate/free churn fragments the pool and occasionally stalls a fit for hundreds of milliseconds.
+  int borrow(DevBuf& cache, size_t count) {
+    release();
+    int rc = cache.ensure(count);
+    if (rc != BK_OK) return rc;
+    p = cache.p;
+    n = count;
+    borrowed = true;
+    return BK_OK;
+  }
+  bool borrowed = false;
 };
 
 struct Timer {
@@ -136,6 +155,8 @@ struct bk_ctx {
   bk::DevBuf<double> gemm_ws;          // split-K partials
   bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
   bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
+  bk::DevBuf<double> ws[5];            // cached N x N work matrices of the eigensolver (0 work copy of K,
+                                       // 1 stage-2 reflectors, 2-4 divide & conquer), released by bk_trim / bk_destroy
   uint64_t n_launches = 0;             // kernels launched through this context (bench "gpu_launches")
 };
 

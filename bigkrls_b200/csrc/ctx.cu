@@ -65,6 +65,7 @@ void bk_destroy(bk_ctx* ctx) {
   ctx->gemm_ws.release();
   ctx->barrier.release();
   ctx->scratch.release();
+  for (auto& w : ctx->ws) w.release();
   cudaStreamSynchronize(ctx->stream);
   if (bk::pool_enabled()) {
     cudaMemPool_t pool;
@@ -74,6 +75,21 @@ void bk_destroy(bk_ctx* ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
+}
+
+int bk_trim(bk_ctx* ctx) {
+  BK_REQUIRE(ctx != nullptr, "bk_trim: ctx is NULL");
+  BK_CUDA(bk::bind_ctx(ctx));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& w : ctx->ws) w.release();
+  ctx->gemm_ws.release();
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (bk::pool_enabled()) {
+    cudaMemPool_t pool;
+    BK_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    BK_CUDA(cudaMemPoolTrimTo(pool, 0));
+  }
+  return BK_OK;
 }
 
 int bk_device_info(bk_ctx* ctx, char* name, int name_len, int* sm_count, int64_t* hbm_total,

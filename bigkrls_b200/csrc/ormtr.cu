@@ -158,7 +158,7 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
   }
   DevBuf<double> d, e, tau, workbuf;
   const long long ldw = sytrd_ld(n);
-  BK_TRY(workbuf.alloc((size_t)ldw * n));
+  BK_TRY(workbuf.borrow(ctx->ws[0], (size_t)ldw * n));
   double* work = workbuf.p;
   BK_CUDA(cudaMemsetAsync(work, 0, sizeof(double) * (size_t)ldw * n, ctx->stream));
   BK_TRY(d.alloc(n));

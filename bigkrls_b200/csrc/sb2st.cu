@@ -748,7 +748,7 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
   ts->n = n;
   ts->maxhops = n / b + 2;
   const int npan = (int)ceil_div(n, b);
-  BK_TRY(ts->work.alloc((size_t)n * n));
+  BK_TRY(ts->work.borrow(ctx->ws[0], (size_t)n * n));
   BK_TRY(ts->AB.alloc((size_t)LDAB * n));
   BK_TRY(ts->Tstore.alloc((size_t)npan * b * b));
   BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
@@ -757,7 +757,7 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
   BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, ts->work.p, n));
   BK_TRY(sy2sb(ctx, ts->work.p, n, n, ts->Tstore.p, ts->AB.p, LDAB, &ts->band));
   ts->t_sy2sb = tm.stop();
-  BK_TRY(ts->VV.alloc((size_t)n * n));
+  BK_TRY(ts->VV.borrow(ctx->ws[1], (size_t)n * n));
   tm.start();
   BK_TRY(sb2st(ctx, ts->AB.p, n, d, e, ts->VV.p, ts->TAU.p, ts->maxhops));
   ts->t_sb2st = tm.stop();

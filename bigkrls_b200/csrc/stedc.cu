@@ -541,7 +541,7 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
   DevBuf<int2> leaves_d;
   DevBuf<MergeDesc> desc_d;
   DevBuf<GemmProb> probs_d;
-  BK_TRY(Q.alloc((size_t)n * n));
+  BK_TRY(Q.borrow(ctx->ws[2], (size_t)n * n));
   BK_TRY(Dcur.alloc(n));
   BK_TRY(Dnew.alloc(n));
   BK_TRY(zv.alloc(n));
@@ -560,8 +560,8 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
     BK_CUDA(cudaGetLastError());
   }
   if (height > 0) {
-    BK_TRY(Gm.alloc((size_t)n * n));
-    BK_TRY(U.alloc((size_t)n * n));
+    BK_TRY(Gm.borrow(ctx->ws[3], (size_t)n * n));
+    BK_TRY(U.borrow(ctx->ws[4], (size_t)n * n));
   }
   std::vector<double> Dh(n), zh(n);
   if (stats) *stats = StedcStats();

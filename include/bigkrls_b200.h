@@ -56,6 +56,9 @@ BK_API int bk_version(void);
 BK_API const char* bk_last_error(void);
 BK_API int bk_init(int device, bk_ctx** out);
 BK_API void bk_destroy(bk_ctx* ctx);
+/* Gives cached device memory back: the eigensolver's work matrices kept in the context between fits and the
+ * unused part of the device memory pool.  Results of live fits are not affected. */
+BK_API int bk_trim(bk_ctx* ctx);
 /* name, SM count, total/free HBM bytes of the context's device */
 BK_API int bk_device_info(bk_ctx* ctx, char* name, int name_len, int* sm_count, int64_t* hbm_total,
                    int64_t* hbm_free);
