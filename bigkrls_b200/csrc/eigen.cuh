@@ -62,6 +62,9 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
           BandStats* stats = nullptr);
 int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops);
 int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz, int k);
+// GEMM-based variant for many columns (q2_blocked.cu): compact-WY blocks of 64 reflectors, batched DMMA GEMMs
+int q2_apply_blocked(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz,
+                     int k);
 int q1_apply(bk_ctx* ctx, const double* A, long long lda, int n, const double* Tstore, double* Z, long long ldz,
              int k);
 struct TwoStage {
@@ -73,6 +76,7 @@ struct TwoStage {
 // K (n x n, only read) -> d, e (device, length n); reflectors kept in ts for twostage_back
 int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e);
 int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k);
+static constexpr int kTwoStageFullMax = 16384;  // largest n for which the two-stage path is taken for ALL vectors
 bool use_twostage(int n, int max_want, double rel_thresh);
 inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
 

@@ -119,7 +119,7 @@ static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int 
   StedcStats st;
   BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
   const double t_dc = tm.stop();
-  if (Z && nw > n / 3 && !getenv("BK_EIG_TWOSTAGE")) {
+  if (Z && nw > n / 3 && n > kTwoStageFullMax && !getenv("BK_EIG_TWOSTAGE")) {
     *too_wide = true;
     return BK_OK;
   }

@@ -768,7 +768,14 @@ int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k) {
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
   tm.start();
-  BK_TRY(q2_apply(ctx, ts->VV.p, ts->TAU.p, ts->maxhops, ts->n, Z, ldz, k));
+  // few columns: sliding-window kernel (each window row crosses shared memory once per 4 reflectors);
+  // many columns: compact-WY blocks on the DMMA GEMM
+  bool blocked = k > 1536;
+  if (const char* f = getenv("BK_Q2_BLOCKED")) blocked = atoi(f) != 0;
+  if (blocked)
+    BK_TRY(q2_apply_blocked(ctx, ts->VV.p, ts->TAU.p, ts->maxhops, ts->n, Z, ldz, k));
+  else
+    BK_TRY(q2_apply(ctx, ts->VV.p, ts->TAU.p, ts->maxhops, ts->n, Z, ldz, k));
   ts->t_q2 = tm.stop();
   tm.start();
   BK_TRY(q1_apply(ctx, ts->work.p, ts->n, ts->n, ts->Tstore.p, Z, ldz, k));
@@ -781,9 +788,14 @@ int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k) {
 // one-stage panels.
 bool use_twostage(int n, int max_want, double rel_thresh) {
   if (const char* f = getenv("BK_EIG_TWOSTAGE")) return atoi(f) != 0;
-  // with a relative eigenvalue threshold (eigtrunc) the number of vectors is only known after the
-  // tridiagonal eigenvalues: go two-stage and let eigen_full fall back if the threshold keeps > n/3
-  return n >= 4096 && n <= 56000 && (max_want <= n / 8 || rel_thresh > 0.0);
+  if (n < 4096 || n > 56000) return false;
+  // few eigenvectors, or an eigenvalue threshold (eigtrunc: the count is only known after the tridiagonal
+  // eigenvalues; eigen_full falls back if the threshold keeps too many at a large n)
+  if (max_want <= n / 8 || rel_thresh > 0.0) return true;
+  // all eigenvectors: with the GEMM-based Q2 the two-stage path still wins up to n ~ 16k (measured at n = 10k:
+  // 0.62 s against 0.79 s); beyond, the 6 n^3 flops of the two back-transformations catch up with the
+  // HBM-bound one-stage panels
+  return n <= kTwoStageFullMax;
 }
 
 }  // namespace bk

@@ -56,6 +56,22 @@ def test_twostage(ctx, n, p, k):
     assert orth < 1e-12 * np.sqrt(n), orth
 
 
+@pytest.mark.parametrize("n,p,k", [(66, 3, 66), (517, 6, 100), (1000, 4, 1000), (3001, 5, 400)])
+def test_q2_blocked_backtransform(ctx, monkeypatch, n, p, k):
+    """The GEMM-based (compact-WY blocks) Q2 back-transformation, forced for every k (odd n: unaligned path)."""
+    monkeypatch.setenv("BK_Q2_BLOCKED", "1")
+    lib = _lib.load()
+    A = kernel_matrix(n, p)
+    d = np.zeros(n)
+    e = np.zeros(n)
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), None, 0, None))
+    lam, S = eigh_tridiagonal(d, e[:n - 1])
+    Z = np.asfortranarray(S[:, n - k:])
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), dptr(Z), k, None))
+    assert np.max(np.abs(A @ Z - Z * lam[n - k:])) < 1e-12 * lam.max() * np.sqrt(n)
+    assert np.max(np.abs(Z.T @ Z - np.eye(k))) < 1e-12 * np.sqrt(n)
+
+
 def test_twostage_matches_onestage_fit(ctx, monkeypatch):
     """The product path gives the same fit with either tridiagonalisation (tolerances of the north star)."""
     from bigkrls_b200 import api
@@ -73,20 +89,43 @@ def test_twostage_matches_onestage_fit(ctx, monkeypatch):
     assert np.max(np.abs(out["0"][2] - out["1"][2])) <= 1e-8 * np.max(np.abs(out["0"][2]))
 
 
-def test_wide_spectrum_falls_back_to_onestage(ctx, monkeypatch):
-    """With an eigenvalue threshold the solver starts two-stage; when the threshold keeps more than n/3
-    eigenvectors (flat spectrum: many dimensions) it must fall back to the one-stage path and give exactly
-    the one-stage result."""
+def test_wide_spectrum_twostage_with_blocked_q2(ctx, monkeypatch):
+    """Flat spectrum (many dimensions): the threshold keeps most eigenvectors; up to n = 16384 the two-stage path
+    keeps going with the GEMM-based Q2 and must agree with the one-stage path within the north-star tolerances."""
     from bigkrls_b200 import api
     X, y = o.synthetic(4200, 40, 3)
     monkeypatch.delenv("BK_EIG_TWOSTAGE", raising=False)
+    monkeypatch.delenv("BK_Q2_BLOCKED", raising=False)
     fit = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False)
     assert fit["lastkeeper"] > 4200 // 3
+    assert fit["_info"]["twostage"] == 1.0
+    c2, lam2, k2 = np.array(fit["coeffs"]).ravel().copy(), fit["lambda"], fit["lastkeeper"]
+    fit.release_device()
+    monkeypatch.setenv("BK_EIG_TWOSTAGE", "0")
+    fit0 = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False)
+    c1 = np.array(fit0["coeffs"]).ravel()
+    assert fit0["lastkeeper"] == k2
+    assert abs(fit0["lambda"] - lam2) <= 1e-9 * abs(lam2)
+    assert np.max(np.abs(c1 - c2)) <= 1e-8 * np.max(np.abs(c1))
+    fit0.release_device()
+
+
+def test_wide_spectrum_falls_back_to_onestage_at_large_n(ctx, monkeypatch):
+    """Above n = 16384 a threshold that keeps more than n/3 eigenvectors sends the solver back to the one-stage
+    path (its back-transformation is a plain GEMM): the result is exactly the one-stage result."""
+    from bigkrls_b200 import api
+    n = 16500
+    X, y = o.synthetic(n, 40, 3)
+    monkeypatch.delenv("BK_EIG_TWOSTAGE", raising=False)
+    fit = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False,
+                      return_squares=False)
+    assert fit["lastkeeper"] > n // 3
     assert fit["_info"]["twostage"] == 0.0
     ref_c, ref_lam = np.array(fit["coeffs"]).copy(), fit["lambda"]
     fit.release_device()
     monkeypatch.setenv("BK_EIG_TWOSTAGE", "0")
-    fit0 = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False)
+    fit0 = api.bigKRLS(y, X, eigtrunc=0.0001, ctx=ctx, noisy=False, derivative=False, vcov_est=False,
+                       return_squares=False)
     assert fit0["lambda"] == ref_lam
     assert np.array_equal(np.array(fit0["coeffs"]), ref_c)
     fit0.release_device()
