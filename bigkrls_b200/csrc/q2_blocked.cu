@@ -118,26 +118,26 @@ int q2_apply_blocked(bk_ctx* ctx, const double* VV, const double* TAU, int maxho
   const int nb = (int)blocks.size();
   if (nb == 0) return BK_OK;
   DevBuf<Q2Block> blocks_d;
-  DevBuf<double> Vb, taub, Sb, Tb, W1, W2;
-  DevBuf<GemmProb> pS_d, p1_d, p2_d, p3_d;
+  DevBuf<double> Vb, Yb, taub, Sb, Tb, W2;
+  DevBuf<GemmProb> pS_d, pY_d, p1_d, p3_d;
   BK_TRY(upload_vec(ctx, blocks_d, blocks));
   BK_TRY(Vb.alloc((size_t)nb * QR * QB));
   BK_TRY(taub.alloc((size_t)nb * QB));
   BK_TRY(Sb.alloc((size_t)nb * QB * QB));
   BK_TRY(Tb.alloc((size_t)nb * QB * QB));
-  BK_TRY(W1.alloc(max_step * QB * (size_t)k));
+  BK_TRY(Yb.alloc((size_t)nb * QR * QB));
   BK_TRY(W2.alloc(max_step * QB * (size_t)k));
   q2b_build_kernel<<<nb, 256, 0, ctx->stream>>>(VV, TAU, maxhops, n, blocks_d.p, Vb.p, taub.p);
   BK_LAUNCHED(ctx);
   // ---- T factors: S = V'V (batched GEMM), then the larft recurrence ---------------------------------------
-  std::vector<GemmProb> pS(nb), p1(nb), p2(nb), p3(nb);
+  std::vector<GemmProb> pS(nb), pY(nb), p1(nb), p3(nb);
   for (int s = 0; s + 1 < (int)step_off.size(); ++s) {
     for (int i = step_off[s]; i < step_off[s + 1]; ++i) {
       const Q2Block& b = blocks[i];
       const int slot = i - step_off[s];
       double* V = Vb.p + (size_t)i * QR * QB;
       double* T = Tb.p + (size_t)i * QB * QB;
-      double* w1 = W1.p + (size_t)slot * QB * k;
+      double* Y = Yb.p + (size_t)i * QR * QB;
       double* w2 = W2.p + (size_t)slot * QB * k;
       double* Zr = Z + b.R0;
       GemmProb g{};
@@ -146,14 +146,14 @@ int q2_apply_blocked(bk_ctx* ctx, const double* VV, const double* TAU, int maxho
       g.A = V; g.lda = QR; g.B = V; g.ldb = QR; g.C = Sb.p + (size_t)i * QB * QB; g.ldc = QB;
       g.m = QB; g.n = QB; g.k = QR; g.alpha = 1.0; g.beta = 0.0;
       pS[i] = g;
-      // W1 = V' Z[R0:R0+rows, :]   (64 x k x rows)
-      g.A = V; g.lda = QR; g.B = Zr; g.ldb = ldz; g.C = w1; g.ldc = QB;
+      // Y = V T'  (128 x 64 x 64): Q Z = Z - V (T V' Z) = Z - V (Y' Z)
+      g.A = V; g.lda = QR; g.B = T; g.ldb = QB; g.C = Y; g.ldc = QR;
+      g.m = QR; g.n = QB; g.k = QB; g.alpha = 1.0; g.beta = 0.0;
+      pY[i] = g;
+      // W2 = Y' Z[R0:R0+rows, :]   (64 x k x rows)
+      g.A = Y; g.lda = QR; g.B = Zr; g.ldb = ldz; g.C = w2; g.ldc = QB;
       g.m = QB; g.n = k; g.k = b.rows; g.alpha = 1.0; g.beta = 0.0;
       p1[i] = g;
-      // W2 = T W1   (64 x k x 64)
-      g.A = T; g.lda = QB; g.B = w1; g.ldb = QB; g.C = w2; g.ldc = QB;
-      g.m = QB; g.n = k; g.k = QB; g.alpha = 1.0; g.beta = 0.0;
-      p2[i] = g;
       // Z[R0:R0+rows, :] -= V W2   (rows x k x 64)
       g.A = V; g.lda = QR; g.B = w2; g.ldb = QB; g.C = Zr; g.ldc = ldz;
       g.m = b.rows; g.n = k; g.k = QB; g.alpha = -1.0; g.beta = 1.0;
@@ -162,7 +162,7 @@ int q2_apply_blocked(bk_ctx* ctx, const double* VV, const double* TAU, int maxho
   }
   BK_TRY(upload_vec(ctx, pS_d, pS));
   BK_TRY(upload_vec(ctx, p1_d, p1));
-  BK_TRY(upload_vec(ctx, p2_d, p2));
+  BK_TRY(upload_vec(ctx, pY_d, pY));
   BK_TRY(upload_vec(ctx, p3_d, p3));
   const bool vecZ = gemm_operands_vec_ok(Z, ldz, Z, ldz);  // R0 is even: block rows keep the alignment of Z
   BK_TRY(gemm_batched(ctx, true, false, pS_d.p, nb, QB, QB, true));
@@ -170,12 +170,12 @@ int q2_apply_blocked(bk_ctx* ctx, const double* VV, const double* TAU, int maxho
                                (int)(sizeof(double) * 2 * QB * QB)));
   q2b_larft_kernel<<<nb, 16 * QB, sizeof(double) * 2 * QB * QB, ctx->stream>>>(Sb.p, taub.p, Tb.p);
   BK_LAUNCHED(ctx);
+  BK_TRY(gemm_batched(ctx, false, true, pY_d.p, nb, QR, QB, true));
   // ---- apply, one batched launch triple per step ------------------------------------------------------------
   for (int s = 0; s + 1 < (int)step_off.size(); ++s) {
     const int o = step_off[s], cnt = step_off[s + 1] - o;
     if (cnt == 0) continue;
     BK_TRY(gemm_batched(ctx, true, false, p1_d.p + o, cnt, QB, k, vecZ));
-    BK_TRY(gemm_batched(ctx, false, false, p2_d.p + o, cnt, QB, k, true));
     BK_TRY(gemm_batched(ctx, false, false, p3_d.p + o, cnt, QR, k, true));
   }
   BK_CUDA(cudaGetLastError());
