@@ -103,3 +103,44 @@ def test_dc_prototype_is_a_valid_eigensolver():
     assert np.max(np.abs(lam - ref)) < 1e-13 * np.max(np.abs(ref)) * 10
     assert np.max(np.abs(Q.T @ Q - np.eye(n))) < 1e-13
     assert np.max(np.abs(T @ Q - Q * lam)) < 1e-13 * np.max(np.abs(ref)) * 10
+
+
+def host_bounds(values, n):
+    lib = _lib.load()
+
+    def cb(user, lams, nlam, out):
+        for i in range(nlam):
+            out[i] = 1.0          # flat loss: the golden section stops at once, only the bounds matter
+        return 0
+
+    cbf = _lib.LE_CALLBACK(cb)
+    lam, L, U = C.c_double(), C.c_double(), C.c_double()
+    probes, passes = C.c_int(), C.c_int()
+    ev = np.ascontiguousarray(values, dtype=np.float64)
+    rc = lib.bk_host_lambda_search(_lib.dptr(ev), len(ev), n, 0.0, 0.0, 0.0, 7, C.cast(cbf, C.c_void_p), None,
+                                   C.byref(lam), C.byref(L), C.byref(U), C.byref(probes), C.byref(passes))
+    return rc, L.value, U.value
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lambda_bounds_bisection_equals_linear_scan(seed):
+    """The upper bound is found by gallop + bisection instead of the reference's `U <- U - 1` scan
+    (R/bigKRLS_Rcpp_functions.R:16-20); it must stop at exactly the same U for any spectrum."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(200, 3000))
+    shape = seed % 3
+    if shape == 0:      # fast geometric decay (Gaussian kernel, few dimensions)
+        ev = n * 0.5 ** np.arange(n) + 1e-14 * rng.random(n)
+    elif shape == 1:    # one dominant value over a flat floor (many dimensions)
+        ev = np.concatenate([[0.15 * n], 0.85 + 0.1 * rng.random(n - 1)])
+    else:               # power law
+        ev = n / (1.0 + np.arange(n)) ** 1.5
+    ev = np.sort(ev)[::-1] * (n / ev.sum())          # trace = n like a unit-diagonal kernel
+    L0, U0 = o.lambda_bounds(ev, n)
+    rc, L, U = host_bounds(ev, n)
+    assert rc == 0 and (L, U) == (L0, U0)
+
+
+def test_lambda_bounds_degenerate_spectrum_is_an_error():
+    rc, _, _ = host_bounds(np.zeros(50), 50)           # sum(ev/(ev+U)) < 1 for every U: the scan never ends
+    assert rc != 0
