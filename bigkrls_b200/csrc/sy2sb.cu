@@ -9,8 +9,11 @@
 //      (partial dot products of the pivot column with the remaining columns -> every CTA forms tau and
 //      the update coefficients redundantly -> updates its own slab).
 //   2. T (compact WY) from V'V;  Z = A22 (V T);  W = Z - 1/2 V (T' (V'Z));  A22 -= [V W][W V]'
-//      on the DMMA GEMM - 6 m^2 b flops per panel, 2 N^3 in total.
-// The matrix is kept fully symmetric (both triangles updated) so that A22 (V T) is a plain GEMM.
+//      on the DMMA GEMM - 4 m^2 b useful flops per panel, (4/3) N^3 in total.  Panels are taken in PAIRS
+//      (see the loop in sy2sb): only the second panel's columns get the first panel's update at once, the
+//      second Z is corrected for the pending update, and one rank-4b update serves both panels.
+// The matrix is kept fully symmetric (lower tiles are computed, the GEMM epilogue writes the transposed tile
+// as well) so that A22 (V T) is a plain GEMM.
 // V is left LAPACK-style below the band of A (unit diagonal implicit) and T_k is stored for the
 // back-transformation.
 #include <cstdlib>
