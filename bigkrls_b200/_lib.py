@@ -121,6 +121,8 @@ _SIGNATURES = {
     "bk_fit_get_var_avgderiv": (C.c_int, [C.c_void_p, c_double_p]),
     "bk_fit_get_binary": (C.c_int, [C.c_void_p, c_int32_p]),
     "bk_fit_predict": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p]),
+    "bk_fit_predict_full": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p,
+                                      c_double_p]),
     "bk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_double_p]),
     "bk_dgemm_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                  C.c_double, C.c_int, c_double_p]),

@@ -63,8 +63,8 @@ def _stop(msg):
 def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None, vcov_est=True,
             Neig=None, eigtrunc=None, lambda_=None, L=None, U=None, tol=None, acf=False,
             noisy=None, instructions=False, ctx=None, comm=None, return_squares=True,
-            keep_device=True, loo_batch=7, fix_sd_index_bug=False, pinned=False, Ncores=None,
-            model_subfolder_name=None, overwrite_existing=False):
+            keep_device=True, loo_batch=15, fix_sd_index_bug=False, pinned=False, Ncores=None,
+            model_subfolder_name=None, overwrite_existing=False, squares_alloc=None):
     """Kernel-regularised least squares, all heavy stages on the GPU.
 
     `which_derivatives` is 1-based like R.  `comm` is a bigkrls_b200.dist.TorchComm for
@@ -133,7 +133,7 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
     opts.eigtrunc = float(eigtrunc)
     opts.neig = Neig_
     opts.lambda_ = float(lambda_) if lambda_ is not None else 0.0
-    opts.L = float(L) if L is not None else 0.0
+    opts.L = float(L) if L is not None else -1.0
     opts.U = float(U) if U is not None else 0.0
     opts.tol = 0.0          # the reference computes tol (:232-236) but never forwards it (:274-275)
     opts.derivative = 1 if derivative else 0
@@ -148,13 +148,22 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
         opts.which = wd0.ctypes.data_as(_lib.c_int32_p)
     h = C.c_void_p()
     cptr = C.byref(comm.struct) if comm is not None and comm.world > 1 else None
-    alloc = (lambda shape: ctx.pinned_empty(shape)) if pinned else (lambda shape: np.empty(shape, order="F"))
+    # where the N x N outputs go: library-pinned buffers, plain (pageable) numpy memory, or anything the caller
+    # provides through squares_alloc(name, shape) -> F-ordered float64 array - e.g. np.memmap files standing in for
+    # the reference's file-backed big.matrix (R/bigKRLS_Rcpp_functions.R:143-147); pageable targets are filled by
+    # the library's bounce-buffer copy engine (csrc/hostcopy.cu)
+    if squares_alloc is not None:
+        alloc = squares_alloc
+    elif pinned:
+        alloc = lambda name, shape: ctx.pinned_empty(shape)
+    else:
+        alloc = lambda name, shape: np.empty(shape, order="F")
     K = None
     if return_squares:
         # the kernel matrix is final after the first stage: hand its host buffer to the library so that the
         # device->host copy runs under the eigensolver instead of after the fit
         rank_, world_ = (comm.rank, comm.world) if cptr is not None else (0, 1)
-        K = alloc((n, n * (rank_ + 1) // world_ - n * rank_ // world_))
+        K = alloc("K", (n, n * (rank_ + 1) // world_ - n * rank_ // world_))
         opts.K_host = K.ctypes.data
     check(lib.bk_fit_run(ctx.handle, dptr(Xs), dptr(ys), n, p, C.byref(opts), cptr, C.byref(h)))
     w._fit, w._ctx = h, ctx
@@ -214,10 +223,10 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
         check(lib.bk_fit_get_K(h, dptr(K)))                                     # no-op: delivered during the fit
         w["K"] = K                                                              # :435
         if vcov_est:
-            Vc = alloc((n, ncols))
+            Vc = alloc("vcov.est.c", (n, ncols))
             check(lib.bk_fit_get_vcov_c(h, dptr(Vc)))
             w["vcov.est.c"] = Vc                                                # :439-452
-            Vf = alloc((n, ncols))
+            Vf = alloc("vcov.est.fitted", (n, ncols))
             check(lib.bk_fit_get_vcov_fitted(h, dptr(Vf)))
             w["vcov.est.fitted"] = Vf
     w["_pinned"] = bool(pinned)
@@ -227,11 +236,49 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
     return w
 
 
-def predict(object, newdata, se_pred=False, correct_SE=True, ytest=None):
-    """predict.bigKRLS (R/bigKRLS.R:547-637)."""
+def _predict_rows(object, news, se_pred, ctx):
+    """Rows `news` (standardised) -> (pred_std, Knew, se2 | None, G | None) on this process's GPU.
+
+    With the fit's device state alive: the fused path (bk_fit_predict_full, spectral quadratic forms).  Without it
+    (keep_device=False, released, or a fit rebuilt from saved fields) the reference's own recipe on the host
+    fields X, coeffs, vcov.est.c through the per-op entry points (R/bigKRLS.R:599-608)."""
+    lib = _lib.load()
+    X = np.asarray(object["X"], dtype=np.float64)
+    m, n = news.shape[0], X.shape[0]
+    pred = np.empty(m)
+    Knew = np.empty((m, n), order="F")
+    se2 = np.empty(m) if se_pred else None
+    vp = np.empty((m, m), order="F") if se_pred else None
+    if object._fit is not None:
+        check(lib.bk_fit_predict_full(object._fit, dptr(news), m, dptr(pred), dptr(Knew),
+                                      dptr(se2) if se_pred else None, dptr(vp) if se_pred else None))
+        return pred, Knew, se2, vp
+    h = ctx.handle
+    Xs = fmat((X - X.mean(axis=0)) / _col_sd(X))
+    check(lib.bk_temp_kernel(h, dptr(news), m, dptr(Xs), n, X.shape[1], float(object["sigma"]), dptr(Knew)))
+    c = np.ascontiguousarray(object["coeffs"], dtype=np.float64).reshape(-1)
+    check(lib.bk_dgemm(h, 0, 0, m, 1, n, dptr(Knew), m, dptr(c), n, dptr(pred), m))
+    if se_pred:
+        V = object["vcov.est.c"]
+        if V.shape != (n, n):
+            raise BKError(-4, "predict(se.pred=TRUE) from host fields needs the full vcov.est.c (this is a column "
+                              "block of a multi-GPU fit)")
+        V = np.asfortranarray(V)
+        T = np.empty((m, n), order="F")
+        check(lib.bk_dgemm(h, 0, 0, m, n, n, dptr(Knew), m, dptr(V), n, dptr(T), m))      # newdataK %*% vcov.est.c
+        check(lib.bk_dgemm(h, 0, 1, m, m, n, dptr(T), m, dptr(Knew), m, dptr(vp), m))     # bTCrossProd(., newdataK)
+        se2 = np.diag(vp).copy()
+    return pred, Knew, se2, vp
+
+
+def predict(object, newdata, se_pred=False, correct_SE=True, ytest=None, comm=None):
+    """predict.bigKRLS (R/bigKRLS.R:547-637).  Returns the reference's list fields: predicted, se.pred,
+    vcov.est.pred, newdata, newdataK, has.big.matrices, ytest.
+
+    With a multi-rank `comm` the rows of newdata are sharded over the ranks (independent rows, SURVEY 8e-S6);
+    every rank returns the gathered full result."""
     if not isinstance(object, BigKRLS):
         raise TypeError("Object not of class 'bigKRLS'")
-    lib = _lib.load()
     X = np.asarray(object["X"], dtype=np.float64)
     new = np.asarray(newdata, dtype=np.float64)
     if new.ndim == 1:
@@ -244,20 +291,35 @@ def predict(object, newdata, se_pred=False, correct_SE=True, ytest=None):
     news = fmat((new - Xmeans) / Xsd)                                           # :593-594
     m, n = news.shape[0], X.shape[0]
     y = np.asarray(object["y"]).reshape(-1)
-    if object._fit is None:
-        raise BKError(-4, "predict: the fit's device state was released; refit with keep_device=True")
-    pred = np.empty(m)
-    Knew = np.empty((m, n), order="F")
-    se2 = np.empty(m) if se_pred else None
-    check(lib.bk_fit_predict(object._fit, dptr(news), m, dptr(pred), dptr(Knew),
-                             dptr(se2) if se_pred else None))
+    ctx = object._ctx or _lib.default_context()
+    world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
+    if world > 1:
+        r0, r1 = m * rank // world, m * (rank + 1) // world
+        part = _predict_rows(object, fmat(news[r0:r1]), se_pred, ctx) if r1 > r0 else None
+        parts = comm.gather_objects((r0, r1, part))
+        pred, Knew = np.empty(m), np.empty((m, n), order="F")
+        se2 = np.empty(m) if se_pred else None
+        for a, b, pt in parts:
+            if pt is not None:
+                pred[a:b], Knew[a:b] = pt[0], pt[1]
+                if se_pred:
+                    se2[a:b] = pt[2]
+        vp = None
+        if se_pred:
+            # off-diagonal blocks couple rows of different ranks: the M x M matrix from the gathered kernel rows
+            _, _, _, vp = _predict_rows(object, news, True, ctx) if rank == 0 else (None, None, None, None)
+            vp = comm.broadcast_object(vp, 0)
+    else:
+        pred, Knew, se2, vp = _predict_rows(object, news, se_pred, ctx)
     out = {"predicted": pred * np.std(y, ddof=1) + y.mean(),                    # :618
            "se.pred": None, "vcov.est.pred": None, "newdata": newdata, "newdataK": Knew,
            "has.big.matrices": object["has.big.matrices"], "ytest": ytest}
     if se_pred:
         v = se2.copy()
         if correct_SE and object.get("Neffective") is not None:
-            v = math.sqrt(n / object["Neffective"]) * v                         # :610-611
+            f = math.sqrt(n / object["Neffective"])                             # :610-611
+            v, vp = f * v, f * vp
+        out["vcov.est.pred"] = vp                                               # :605
         out["se.pred"] = np.sqrt(v).reshape(-1, 1)                              # :613
     return out
 

@@ -170,23 +170,25 @@ int bk_deriv_mat(bk_ctx* ctx, const double* X, int64_t n, int64_t p, const doubl
   BK_TRY(enter(ctx, "bk_deriv_mat"));
   BK_REQUIRE(X && K && V && coeffs && D && var && n > 0 && p > 0 && fits_int(n) && fits_int(p),
              "bk_deriv_mat: bad arguments");
-  const int ni = (int)n, pi = (int)p, m = 2 * pi + 2;
+  const int ni = (int)n, pi = (int)p;
+  int nbin = 0;
   DevBuf<double> dX, dK, dV, dc, info, W, KW, dD, dR, VR, dvar;
   BK_TRY(h2d(ctx, dX, X, (size_t)n * p));
   BK_TRY(h2d(ctx, dK, K, (size_t)n * n));
   BK_TRY(h2d(ctx, dV, V, (size_t)n * n));
   BK_TRY(h2d(ctx, dc, coeffs, (size_t)n));
-  BK_TRY(info.alloc(3 * p));
+  BK_TRY(info.alloc(4 * p + 1));
+  BK_TRY(column_binary_info(ctx, dX.p, n, ni, pi, info.p, &nbin));
+  const int m = 2 * pi + 2 + 2 * nbin;
   BK_TRY(W.alloc((size_t)n * m));
   BK_TRY(KW.alloc((size_t)n * m));
   BK_TRY(dD.alloc((size_t)n * p));
   BK_TRY(dR.alloc((size_t)n * p));
   BK_TRY(VR.alloc((size_t)n * p));
   BK_TRY(dvar.alloc(p));
-  BK_TRY(column_binary_info(ctx, dX.p, n, ni, pi, info.p));
-  BK_TRY(build_kpass_rhs(ctx, dX.p, n, ni, pi, dc.p, info.p, W.p, n));
+  BK_TRY(build_kpass_rhs(ctx, dX.p, n, ni, pi, nbin, dc.p, info.p, W.p, n));
   BK_TRY(gemm(ctx, false, false, ni, m, ni, 1.0, dK.p, n, W.p, n, 0.0, KW.p, n));
-  BK_TRY(deriv_epilogue(ctx, dX.p, n, ni, pi, KW.p, n, info.p, sigma, dD.p, n, dR.p, n));
+  BK_TRY(deriv_epilogue(ctx, dX.p, n, ni, pi, nbin, KW.p, n, info.p, sigma, dD.p, n, dR.p, n));
   BK_TRY(gemm(ctx, false, false, ni, pi, ni, 1.0, dV.p, n, dR.p, n, 0.0, VR.p, n));
   BK_TRY(deriv_variance_dense(ctx, dR.p, n, VR.p, n, ni, pi, info.p, sigma, dvar.p));
   BK_TRY(d2h(ctx, D, dD.p, (size_t)n * p));

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <stdarg.h>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/bigkrls_b200.h"
@@ -144,6 +145,12 @@ struct Timer {
   }
 };
 
+// device -> host delivery into caller-owned (possibly pageable) memory, hostcopy.cu
+struct HostCopier;
+struct CopyTicket {
+  std::shared_ptr<void> job;
+};
+
 }  // namespace bk
 
 struct bk_ctx {
@@ -155,9 +162,11 @@ struct bk_ctx {
   bk::DevBuf<double> gemm_ws;          // split-K partials
   bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
   bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
+  bk::DevBuf<unsigned int> counters;   // 64 arrival counters, zero between kernels (last-CTA-done reductions)
   bk::DevBuf<double> ws[5];            // cached N x N work matrices of the eigensolver (0 work copy of K,
                                        // 1 stage-2 reflectors, 2-4 divide & conquer), released by bk_trim / bk_destroy
   uint64_t n_launches = 0;             // kernels launched through this context (bench "gpu_launches")
+  bk::HostCopier* copier = nullptr;    // hostcopy.cu
 };
 
 namespace bk {
@@ -253,6 +262,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 }
 
 #endif  // __CUDACC__
+
+HostCopier* copier_create(int device, cudaStream_t copy_stream);
+void copier_destroy(HostCopier* c);
+int copier_submit(bk_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t after, CopyTicket* out);
+int copier_wait(CopyTicket* t);
+int copy_to_host(bk_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t after);
 
 // launch-count bookkeeping
 #define BK_LAUNCHED(ctx) ((ctx)->n_launches++)

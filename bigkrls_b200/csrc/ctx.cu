@@ -53,6 +53,9 @@ int bk_init(int device, bk_ctx** out) {
     BK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   bk::alloc_stream() = c->stream;
+  c->copier = bk::copier_create(device, c->copy_stream);
+  BK_TRY(c->counters.alloc(64));
+  BK_CUDA(cudaMemsetAsync(c->counters.p, 0, 64 * sizeof(unsigned), c->stream));
   *out = c;
   return BK_OK;
 }
@@ -62,9 +65,12 @@ void bk_destroy(bk_ctx* ctx) {
   bk::bind_ctx(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  bk::copier_destroy(ctx->copier);
+  ctx->copier = nullptr;
   ctx->gemm_ws.release();
   ctx->barrier.release();
   ctx->scratch.release();
+  ctx->counters.release();
   for (auto& w : ctx->ws) w.release();
   cudaStreamSynchronize(ctx->stream);
   if (bk::pool_enabled()) {

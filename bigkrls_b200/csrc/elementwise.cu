@@ -136,21 +136,43 @@ __global__ void column_binary_kernel(const double* __restrict__ X, long long ldx
   }
   other = block_sum(other, red);
   if (threadIdx.x == 0) {
-    info[3 * blockIdx.x + 0] = mn;
-    info[3 * blockIdx.x + 1] = mx;
-    info[3 * blockIdx.x + 2] = (other == 0.0 && mn != mx) ? 1.0 : 0.0;
+    info[4 * blockIdx.x + 0] = mn;
+    info[4 * blockIdx.x + 1] = mx;
+    info[4 * blockIdx.x + 2] = (other == 0.0 && mn != mx) ? 1.0 : 0.0;
   }
 }
-int column_binary_info(bk_ctx* ctx, const double* X, long long ldx, int n, int p, double* info) {
+// info[4j+3] = rank of column j among the binary columns (their extra K-pass columns), info[4p] = their number
+__global__ void binary_slots_kernel(double* __restrict__ info, int p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int s = 0;
+  for (int j = 0; j < p; ++j) {
+    const bool b = info[4 * j + 2] != 0.0;
+    info[4 * j + 3] = b ? (double)s : -1.0;
+    s += b ? 1 : 0;
+  }
+  info[4 * p] = (double)s;
+}
+int column_binary_info(bk_ctx* ctx, const double* X, long long ldx, int n, int p, double* info, int* nbin_host) {
+  *nbin_host = 0;
   if (p <= 0) return BK_OK;
   column_binary_kernel<<<p, 256, 0, ctx->stream>>>(X, ldx, n, info);
   BK_LAUNCHED(ctx);
+  binary_slots_kernel<<<1, 32, 0, ctx->stream>>>(info, p);
+  BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
+  double nb = 0.0;
+  BK_CUDA(cudaMemcpyAsync(&nb, info + 4 * p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  *nbin_host = (int)nb;
   return BK_OK;
 }
 
 // ---- K-pass right-hand sides ----------------------------------------------------------------
-__global__ void build_rhs_kernel(const double* __restrict__ X, long long ldx, int n, int p,
+// Binary columns carry BOTH indicator pairs, [x == z1] and [x == z0]: the sums over the z0 group must not be
+// formed as (sum over all) - (sum over the z1 group) - for a rare category (a state dummy with one county) the
+// z0-group sum seen from a z1 row is ~exp(-dz^2/sigma) ~ 1e-20 of the total and is later multiplied by
+// exp(+dz^2/sigma); the subtraction would leave rounding noise times 1e20.
+__global__ void build_rhs_kernel(const double* __restrict__ X, long long ldx, int n, int p, int nbin,
                                  const double* __restrict__ c, const double* __restrict__ info,
                                  double* __restrict__ W, long long ldw) {
   const long long total = (long long)n * (p + 1);
@@ -163,23 +185,29 @@ __global__ void build_rhs_kernel(const double* __restrict__ X, long long ldx, in
       W[r + ldw] = ci;
     } else {
       double v = X[r + (long long)j * ldx];
-      if (info[3 * j + 2] != 0.0) v = (v == info[3 * j + 1]) ? 1.0 : 0.0;
+      if (info[4 * j + 2] != 0.0) {
+        const int s = (int)info[4 * j + 3];
+        const double b0 = (v == info[4 * j + 0]) ? 1.0 : 0.0;
+        v = (v == info[4 * j + 1]) ? 1.0 : 0.0;
+        W[r + (long long)(2 + 2 * p + s) * ldw] = b0;
+        W[r + (long long)(2 + 2 * p + nbin + s) * ldw] = b0 * ci;
+      }
       W[r + (long long)(2 + j) * ldw] = v;
       W[r + (long long)(2 + p + j) * ldw] = v * ci;
     }
   }
 }
-int build_kpass_rhs(bk_ctx* ctx, const double* X, long long ldx, int n, int p, const double* c,
+int build_kpass_rhs(bk_ctx* ctx, const double* X, long long ldx, int n, int p, int nbin, const double* c,
                     const double* info, double* W, long long ldw) {
   build_rhs_kernel<<<grid_for((long long)n * (p + 1), 256, 16 * ctx->sm_count), 256, 0,
-                     ctx->stream>>>(X, ldx, n, p, c, info, W, ldw);
+                     ctx->stream>>>(X, ldx, n, p, nbin, c, info, W, ldw);
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   return BK_OK;
 }
 
 // ---- marginal-effects epilogue --------------------------------------------------------------
-__global__ void deriv_epilogue_kernel(const double* __restrict__ X, long long ldx, int n, int p,
+__global__ void deriv_epilogue_kernel(const double* __restrict__ X, long long ldx, int n, int p, int nbin,
                                       const double* __restrict__ KW, long long ldkw,
                                       const double* __restrict__ info, double sigma,
                                       double* __restrict__ D, long long ldd,
@@ -193,20 +221,23 @@ __global__ void deriv_epilogue_kernel(const double* __restrict__ X, long long ld
     const double Bc = KW[i + (long long)(2 + p + j) * ldkw];
     const double x = X[i + (long long)j * ldx];
     double d, r;
-    if (info[3 * j + 2] == 0.0) {
+    if (info[4 * j + 2] == 0.0) {
       // continuous, src/bigderiv_v3.cpp:90-106:  L = (x_kj - x_ij) o K ; D = (-2/sigma) L c
       d = (-2.0 / sigma) * (x * Kc - Bc);
       r = x * K1 - A;
     } else {
       // binary, src/bigderiv_v3.cpp:31-87
-      const double z0 = info[3 * j + 0], z1 = info[3 * j + 1];
+      const double z0 = info[4 * j + 0], z1 = info[4 * j + 1];
+      const int sl = (int)info[4 * j + 3];
       const double sd = 1.0 / (z1 - z0);                  // :36
       const double phi = -1.0 / (sd * sd * sigma);        // :37
       const double dz = z1 - z0;
       const double e1 = exp(-(dz * dz) / sigma);          // c2 when both rows share the value (:69)
       const double e2 = exp((dz * dz) / sigma);           // c2 otherwise
       const double ep = exp(phi), em = exp(-phi);
-      const double S1 = A, S0 = K1 - A, C1 = Bc, C0 = Kc - Bc;
+      const double S1 = A, C1 = Bc;   // sums over the z1 group; the z0 group has its own columns (see build_rhs_kernel)
+      const double S0 = KW[i + (long long)(2 + 2 * p + sl) * ldkw];
+      const double C0 = KW[i + (long long)(2 + 2 * p + nbin + sl) * ldkw];
       if (x == z0) {
         d = -sd * ((1.0 - e1) * C0 + (1.0 - e2) * C1);
         r = (ep - 1.0) * S0 + (1.0 - em) * S1;
@@ -219,11 +250,11 @@ __global__ void deriv_epilogue_kernel(const double* __restrict__ X, long long ld
     R[i + (long long)j * ldr] = r;
   }
 }
-int deriv_epilogue(bk_ctx* ctx, const double* X, long long ldx, int n, int p, const double* KW,
+int deriv_epilogue(bk_ctx* ctx, const double* X, long long ldx, int n, int p, int nbin, const double* KW,
                    long long ldkw, const double* info, double sigma, double* D, long long ldd,
                    double* R, long long ldr) {
   deriv_epilogue_kernel<<<grid_for((long long)n * p, 256, 16 * ctx->sm_count), 256, 0,
-                          ctx->stream>>>(X, ldx, n, p, KW, ldkw, info, sigma, D, ldd, R, ldr);
+                          ctx->stream>>>(X, ldx, n, p, nbin, KW, ldkw, info, sigma, D, ldd, R, ldr);
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   return BK_OK;
@@ -231,8 +262,8 @@ int deriv_epilogue(bk_ctx* ctx, const double* X, long long ldx, int n, int p, co
 
 __device__ __forceinline__ double var_factor(const double* info, int j, double sigma, int n) {
   const double nn = (double)n * (double)n;
-  if (info[3 * j + 2] == 0.0) return (1.0 / nn) * ((-2.0 / sigma) * (-2.0 / sigma));  // :105
-  const double sd = 1.0 / (info[3 * j + 1] - info[3 * j + 0]);
+  if (info[4 * j + 2] == 0.0) return (1.0 / nn) * ((-2.0 / sigma) * (-2.0 / sigma));  // :105
+  const double sd = 1.0 / (info[4 * j + 1] - info[4 * j + 0]);
   return 2.0 * sd * sd / nn;                                                           // :85
 }
 

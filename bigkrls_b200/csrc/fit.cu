@@ -41,11 +41,9 @@ struct bk_fit {
   bk_fit_info info;
   DevBuf<double> X, y, K, Q, ev, w, c, yhat, sig2, Vc, Vf, D, var, binfo;
   bool have_vcov = false, have_vf = false, have_deriv = false;
-  const double* K_host_done = nullptr;  // host buffer that already holds K (early D2H on the copy stream)
-  bool copy_pending = false;
-  ~bk_fit() {
-    if (copy_pending && ctx) cudaStreamSynchronize(ctx->copy_stream);  // K must outlive the queued copy
-  }
+  const double* K_host_done = nullptr;  // host buffer that already holds K (early D2H under the eigensolver)
+  bk::CopyTicket k_copy;
+  ~bk_fit() { bk::copier_wait(&k_copy); }  // K must outlive the queued copy
 };
 
 namespace {
@@ -66,15 +64,44 @@ long double ratio_sum(const std::vector<double>& ev, double x) {
   for (double e : ev) s += (long double)(e / (e + x));
   return s;
 }
+// The same sum in plain double with eight independent accumulators (vectorisable; ~15 us at Neig = 20 000
+// against ~60 us for the dependent long-double chain).  Its error is bounded by (Neig/8) eps sum|terms|.
+double ratio_sum_fast(const std::vector<double>& ev, double x, double* abs_terms) {
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const size_t n = ev.size(), n8 = n & ~(size_t)7;
+  for (size_t i = 0; i < n8; i += 8)
+    for (int j = 0; j < 8; ++j) {
+      const double t = ev[i + j] / (ev[i + j] + x);
+      s[j] += t;
+      a[j] += std::fabs(t);
+    }
+  for (size_t i = n8; i < n; ++i) {
+    const double t = ev[i] / (ev[i] + x);
+    s[0] += t;
+    a[0] += std::fabs(t);
+  }
+  *abs_terms = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+// sign of (R's sum(ev/(ev+x)) - thr): -1 below, 0 equal, +1 above.  Decided by the fast sum whenever it is
+// further from the threshold than its own error bound (plus the long-double sum's), otherwise by the reference's
+// arithmetic itself - so every comparison of the bounds loops has exactly the outcome R would get.
+int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
+  double at = 0.0;
+  const double f = ratio_sum_fast(ev, x, &at);
+  const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 8 + 8) * at + 1e-13 * std::fabs(thr);
+  if (std::isfinite(f) && std::fabs(f - thr) > band) return f < thr ? -1 : 1;
+  const double s = (double)ratio_sum(ev, x);
+  return s < thr ? -1 : (s > thr ? 1 : 0);
+}
 
 int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
-  if (*U <= 0.0) {
+  if (!(*U > 0.0)) {
     // Reference (R/bigKRLS_Rcpp_functions.R:16-20): U = n; while (sum(ev/(ev+U)) < 1) U = U - 1 - hundreds to
     // thousands of O(Neig) sums.  f(U) = sum(ev/(ev+U)) is strictly decreasing with f(U) - f(U+1) ~ 1/U, many
     // orders above the rounding of the sum, so the first integer step m with f(n-m) >= 1 is found by bisection
-    // and then checked against the scan's stopping rule (f(n-m) >= 1 and f(n-m+1) < 1); the sums themselves are
-    // evaluated exactly as before.
-    auto ok = [&](long long m) { return !((double)ratio_sum(ev, (double)n - (double)m) < 1.0); };
+    // and is exactly where the scan stops (f(n-m) >= 1 and f(n-m+1) < 1).
+    auto ok = [&](long long m) { return ratio_cmp(ev, (double)n - (double)m, 1.0) >= 0; };
     long long lo = 0, hi = -1;
     if (ok(0)) {
       hi = 0;
@@ -101,8 +128,10 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
     }
     *U = (double)n - (double)hi;
   }
-  if (*L <= 0.0) {
-    double l = 2.220446049250313e-16;  // .Machine$double.eps (R/bigKRLS_Rcpp_functions.R:28)
+  if (!(*L >= 0.0)) {  // negative or NaN = not supplied (a user L = 0 is legal, R/bigKRLS.R:225-228)
+    // Reference (:26-36): L = eps; q = which.min(abs(ev - max(ev)/1000)); while (sum(ev/(ev+L)) > q) L = L + 0.05.
+    // The candidates are the partial sums l_0 = eps, l_i = fl(l_{i-1} + 0.05) exactly as the scan forms them;
+    // sum(ev/(ev+l)) decreases along them, so the first index that fails the loop test is found by gallop + bisection.
     const double emax = *std::max_element(ev.begin(), ev.end());
     int q = 0;
     double best = INFINITY;
@@ -113,15 +142,34 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
         q = (int)i + 1;  // which.min: 1-based, first minimum
       }
     }
-    int guard = 0;
-    while ((double)ratio_sum(ev, l) > (double)q) {
-      l += 0.05;
-      if (++guard > 100000000) {
-        set_error("lambda search: lower bound loop did not terminate");
-        return BK_ERR_NUMERIC;
+    std::vector<double> ls{2.220446049250313e-16};  // .Machine$double.eps (:28)
+    auto cand = [&](size_t i) {
+      while (ls.size() <= i) ls.push_back(ls.back() + 0.05);
+      return ls[i];
+    };
+    auto stop = [&](size_t i) { return ratio_cmp(ev, cand(i), (double)q) <= 0; };  // loop test false
+    size_t lo = 0, hi = 0;
+    if (!stop(0)) {
+      size_t step = 1;
+      for (;;) {
+        const size_t m = lo + step;
+        if (m > 100000000u) {
+          set_error("lambda search: lower bound loop did not terminate");
+          return BK_ERR_NUMERIC;
+        }
+        if (stop(m)) {
+          hi = m;
+          break;
+        }
+        lo = m;
+        step *= 2;
+      }
+      while (hi - lo > 1) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (stop(mid)) hi = mid; else lo = mid;
       }
     }
-    *L = l;
+    *L = cand(hi);
   }
   return BK_OK;
 }
@@ -212,11 +260,14 @@ int lambda_search(LooEvaluator& ev, double L, double U, double tol, double* lam_
   BK_TRY(ev.get(s.X1, s, {s.X2}, &S1));
   BK_TRY(ev.get(s.X2, s, {}, &S2));
   int np = 2;
+  auto finite = [&]() {
+    if (std::isfinite(S1) && std::isfinite(S2)) return true;
+    // R: `while (abs(S1 - S2) > tol)` stops with "missing value where TRUE/FALSE needed"
+    set_error("lambda search: leave-one-out loss is not finite (NaN in y, or a zero diagonal of the inverse)");
+    return false;
+  };
+  if (!finite()) return BK_ERR_NUMERIC;
   while (std::fabs(S1 - S2) > tol) {  // :54
-    if (!std::isfinite(S1) || !std::isfinite(S2)) {
-      set_error("lambda search: leave-one-out loss is not finite");
-      return BK_ERR_NUMERIC;
-    }
     if (S1 < S2) {
       const double x = gs_step(s, true);
       S2 = S1;
@@ -226,6 +277,7 @@ int lambda_search(LooEvaluator& ev, double L, double U, double tol, double* lam_
       S1 = S2;
       BK_TRY(ev.get(x, s, {}, &S2));
     }
+    if (!finite()) return BK_ERR_NUMERIC;
     if (++np > 10000) {
       set_error("lambda search: no convergence after 10000 probes");
       return BK_ERR_NUMERIC;
@@ -267,16 +319,11 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     COMM_CALL(comm->allgatherv(comm->user, f->K.p, counts.data(), displs.data()), "allgatherv(K)");
   }
   f->info.t_kernel = tm.stop();
-  cudaEvent_t k_ready = nullptr;
   if (o.K_host) {
-    // K is final: send this rank's column block to the host now, under the eigensolver
-    BK_CUDA(cudaEventCreateWithFlags(&k_ready, cudaEventDisableTiming));
-    BK_CUDA(cudaEventRecord(k_ready, ctx->stream));
-    BK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, k_ready, 0));
-    f->copy_pending = true;
-    BK_CUDA(cudaMemcpyAsync(o.K_host, f->K.p + (long long)f->c0 * ld, sizeof(double) * (size_t)n * (f->c1 - f->c0),
-                            cudaMemcpyDeviceToHost, ctx->copy_stream));
-    cudaEventDestroy(k_ready);
+    // K is final: send this rank's column block to the host now, under the eigensolver (pinned destination: one
+    // DMA on the copy stream; pageable big.matrix memory: the copy engine's bounce lanes, hostcopy.cu)
+    BK_TRY(copier_submit(ctx, o.K_host, f->K.p + (long long)f->c0 * ld, sizeof(double) * (size_t)n * (f->c1 - f->c0),
+                         ctx->stream, &f->k_copy));
   }
 
   // ---- 2/5 eigen ----------------------------------------------------------------------------
@@ -383,7 +430,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
       BK_CUDA(cudaStreamSynchronize(ctx->stream));
       return BK_OK;
     };
-    le.batch = std::max(1, std::min(15, o.loo_batch > 0 ? o.loo_batch : 7));
+    le.batch = std::max(1, std::min(15, o.loo_batch > 0 ? o.loo_batch : 15));
     BK_TRY(lambda_search(le, L, U, tol, &lam, &f->n_probes));
     f->n_passes = le.passes;
   }
@@ -413,9 +460,9 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
 
   // K-pass: KW = K [1 c {x_j|b_j} {x_j c|b_j c}] ; column 1 is yhat = K c  (R/bigKRLS.R:291)
   const int pd = o.derivative ? f->pd : 0;
-  const int mw = 2 * pd + 2;
+  int nbin = 0;
   DevBuf<double> Xd, W, KW;
-  BK_TRY(f->binfo.alloc(3 * std::max(1, pd)));
+  BK_TRY(f->binfo.alloc(4 * std::max(1, pd) + 1));
   if (pd > 0) {
     BK_TRY(Xd.alloc((size_t)n * pd));
     std::vector<int> wh(f->which);
@@ -423,12 +470,12 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     BK_TRY(whd.alloc(pd));
     BK_CUDA(cudaMemcpyAsync(whd.p, wh.data(), sizeof(int) * pd, cudaMemcpyHostToDevice, ctx->stream));
     BK_TRY(gather_columns(ctx, f->X.p, ld, n, pd, whd.p, Xd.p, ld));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    BK_TRY(column_binary_info(ctx, Xd.p, ld, n, pd, f->binfo.p));
+    BK_TRY(column_binary_info(ctx, Xd.p, ld, n, pd, f->binfo.p, &nbin));  // synchronises (wh, whd are temporaries)
   }
+  const int mw = 2 * pd + 2 + 2 * nbin;
   BK_TRY(W.alloc((size_t)n * mw));
   BK_TRY(KW.alloc((size_t)n * mw));
-  BK_TRY(build_kpass_rhs(ctx, Xd.p, ld, n, pd, f->c.p, f->binfo.p, W.p, ld));
+  BK_TRY(build_kpass_rhs(ctx, Xd.p, ld, n, pd, nbin, f->c.p, f->binfo.p, W.p, ld));
   // rows [c0, c1) of K W = (K[:, c0:c1])' W     (K symmetric)
   if (!multi)
     BK_TRY(gemm(ctx, false, false, n, mw, n, 1.0, f->K.p, ld, W.p, ld, 0.0, KW.p, ld));
@@ -496,7 +543,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     BK_TRY(R.alloc((size_t)n * pd));
     BK_TRY(G.alloc((size_t)k * pd));
     BK_TRY(f->var.alloc(pd));
-    BK_TRY(deriv_epilogue(ctx, Xd.p + f->c0, ld, nloc, pd, KW.p + f->c0, ld, f->binfo.p, o.sigma,
+    BK_TRY(deriv_epilogue(ctx, Xd.p + f->c0, ld, nloc, pd, nbin, KW.p + f->c0, ld, f->binfo.p, o.sigma,
                           f->D.p + f->c0, ld, R.p + f->c0, ld));
     // G = Q' R (k x pd); r'V r = sigmasq * sum_i w2_i G_i^2
     BK_TRY(gemm(ctx, true, false, k, pd, nloc, 1.0, f->Q.p + f->c0, ld, R.p + f->c0, ld, 0.0, G.p, k));
@@ -526,9 +573,8 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   BK_CUDA(cudaMemcpyAsync(&f->sigmasq, f->sig2.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   f->info.t_deriv = tm.stop();
-  if (f->copy_pending) {
-    BK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-    f->copy_pending = false;
+  if (o.K_host) {
+    BK_TRY(copier_wait(&f->k_copy));
     f->K_host_done = o.K_host;
   }
   f->info.t_total = total.stop();
@@ -614,18 +660,14 @@ int get_block(const bk_fit* f, const DevBuf<double>& buf, bool have, double* hos
   const size_t cnt = (size_t)f->n * (size_t)(f->c1 - f->c0);
   // single-GPU fits hold the full matrix; multi-GPU fits hold only the owned block (Vc, Vf) or
   // the full K (offset to the owned block)
-  BK_CUDA(cudaMemcpyAsync(host, buf.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_CUDA(cudaStreamSynchronize(ctx->stream));
-  return BK_OK;
+  return copy_to_host(ctx, host, buf.p, sizeof(double) * cnt, ctx->stream);
 }
 
 int get_vec(const bk_fit* f, const double* dev, size_t cnt, double* host) {
   BK_REQUIRE(f && host && dev, "getter: NULL argument or field not computed");
   bk_ctx* ctx = f->ctx;
   BK_CUDA(bk::bind_ctx(ctx));
-  BK_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_CUDA(cudaStreamSynchronize(ctx->stream));
-  return BK_OK;
+  return copy_to_host(ctx, host, dev, sizeof(double) * cnt, ctx->stream);
 }
 
 }  // namespace
@@ -638,7 +680,7 @@ void bk_fit_default_opts(bk_fit_opts* o, int64_t n, int64_t p) {
   o->eigtrunc = (n > 3000) ? 0.001 : 0.0;    // R/bigKRLS.R:195-201
   o->neig = n;                               // R/bigKRLS.R:194
   o->lambda = 0.0;
-  o->L = 0.0;
+  o->L = -1.0;  /* not supplied */
   o->U = 0.0;
   o->tol = 0.0;
   o->derivative = 1;
@@ -646,7 +688,7 @@ void bk_fit_default_opts(bk_fit_opts* o, int64_t n, int64_t p) {
   o->n_which = 0;
   o->which = nullptr;
   o->y_sd = 1.0;
-  o->loo_batch = 7;
+  o->loo_batch = 15;
   o->keep_vcov_fitted = 1;
   o->K_host = nullptr;
 }
@@ -726,14 +768,14 @@ int bk_fit_get_binary(const bk_fit* f, int32_t* host) {
     set_error("derivatives were not computed for this fit");
     return BK_ERR_STATE;
   }
-  std::vector<double> info(3 * f->pd);
-  BK_TRY(get_vec(f, f->binfo.p, 3 * f->pd, info.data()));
-  for (int j = 0; j < f->pd; ++j) host[j] = info[3 * j + 2] != 0.0;
+  std::vector<double> info(4 * f->pd);
+  BK_TRY(get_vec(f, f->binfo.p, 4 * f->pd, info.data()));
+  for (int j = 0; j < f->pd; ++j) host[j] = info[4 * j + 2] != 0.0;
   return BK_OK;
 }
 
-int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred_std, double* Knew,
-                   double* se2) {
+int bk_fit_predict_full(const bk_fit* f, const double* newXs, int64_t m, double* pred_std, double* Knew,
+                        double* se2, double* vcov_pred) {
   BK_REQUIRE(f && newXs && pred_std && m > 0 && m < 2147483647LL, "bk_fit_predict: bad arguments");
   bk_ctx* ctx = f->ctx;
   BK_CUDA(bk::bind_ctx(ctx));
@@ -747,22 +789,39 @@ int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred
   BK_TRY(gauss_kernel_rect(ctx, dN.p, m, mi, f->X.p, n, n, p, f->opts.sigma, dK.p, m));
   BK_TRY(gemm(ctx, false, false, mi, 1, n, 1.0, dK.p, m, f->c.p, n, 0.0, dp.p, m));
   BK_CUDA(cudaMemcpyAsync(pred_std, dp.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-  if (Knew)
-    BK_CUDA(cudaMemcpyAsync(Knew, dK.p, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (se2) {
-    // diag(Knew V Knew') with V = y_sd^2 sigmasq Q (ev+lam)^-2 Q'   (R/bigKRLS.R:608)
+  if (Knew) BK_TRY(copy_to_host(ctx, Knew, dK.p, sizeof(double) * (size_t)m * n, ctx->stream));
+  if (se2 || vcov_pred) {
+    BK_REQUIRE(f->sig2.p != nullptr, "recompute bigKRLS object with bigKRLS(,vcov.est=TRUE) to compute standard errors");
+    // Knew V Knew' with V = y_sd^2 sigmasq Q (ev+lam)^-2 Q'   (R/bigKRLS.R:605-613): G = Knew Q (m x k),
+    // vcov.est.pred = y_sd^2 sigmasq G diag(w2) G', se.pred^2 = its diagonal
     DevBuf<double> G, w2, s2;
+    const double ys2 = f->opts.y_sd * f->opts.y_sd;
     BK_TRY(G.alloc((size_t)m * k));
     BK_TRY(w2.alloc(k));
-    BK_TRY(s2.alloc(m));
     BK_TRY(spectral_weights(ctx, f->ev.p, k, f->lambda, 1, w2.p));
     BK_TRY(gemm(ctx, false, false, mi, k, n, 1.0, dK.p, m, f->Q.p, n, 0.0, G.p, m));
-    BK_TRY(row_quadform(ctx, G.p, m, mi, k, w2.p, f->sig2.p, f->opts.y_sd * f->opts.y_sd, s2.p));
-    BK_CUDA(cudaMemcpyAsync(se2, s2.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (se2) {
+      BK_TRY(s2.alloc(m));
+      BK_TRY(row_quadform(ctx, G.p, m, mi, k, w2.p, f->sig2.p, ys2, s2.p));
+      BK_CUDA(cudaMemcpyAsync(se2, s2.p, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (vcov_pred) {
+      DevBuf<double> M, VP;
+      BK_TRY(M.alloc((size_t)m * k));
+      BK_TRY(VP.alloc((size_t)m * m));
+      BK_TRY(col_scale(ctx, G.p, m, mi, k, w2.p, f->sig2.p, M.p, m));
+      BK_TRY(gemm(ctx, false, true, mi, mi, k, ys2, M.p, m, G.p, m, 0.0, VP.p, m, true));
+      BK_TRY(symmetrize_from_lower(ctx, VP.p, m, mi));
+      BK_TRY(copy_to_host(ctx, vcov_pred, VP.p, sizeof(double) * (size_t)m * m, ctx->stream));
+    }
   }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   return BK_OK;
+}
+
+int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred_std, double* Knew,
+                   double* se2) {
+  return bk_fit_predict_full(f, newXs, m, pred_std, Knew, se2, nullptr);
 }
 
 
@@ -776,7 +835,7 @@ int bk_host_lambda_search(const double* evals, int64_t neig, int64_t n, double L
   if (L_out) *L_out = L;
   if (U_out) *U_out = U;
   LooEvaluator le;
-  le.batch = std::max(1, std::min(15, batch > 0 ? batch : 7));
+  le.batch = std::max(1, std::min(15, batch > 0 ? batch : 15));
   le.eval_batch = [&](const std::vector<double>& lams, double* out) -> int {
     if (cb(user, lams.data(), (int)lams.size(), out) != 0) {
       set_error("bk_host_lambda_search: callback failed");

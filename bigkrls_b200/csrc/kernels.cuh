@@ -19,15 +19,18 @@ int symmetrize_from_lower(bk_ctx* ctx, double* C, long long ldc, int n);
 // d_out[j] = f(ev[j], lambda) for the spectral weights:
 //   mode 0: 1/(ev+lam)   mode 1: 1/(ev+lam)^2   mode 2: (ev/(ev+lam))^2
 int spectral_weights(bk_ctx* ctx, const double* ev, int k, double lam, int mode, double* out);
-// per-column binary detection (src/bigderiv_v3.cpp:28-31): info[3*j+{0,1,2}] = {z0, z1, is_binary}
-int column_binary_info(bk_ctx* ctx, const double* X, long long ldx, int n, int p, double* info);
-// W = [1, c, {x_j or b_j}, {x_j*c or b_j*c}]  (n x (2p+2)), b_j = [x_j == z1_j] for binary columns
-int build_kpass_rhs(bk_ctx* ctx, const double* X, long long ldx, int n, int p, const double* c,
+// per-column binary detection (src/bigderiv_v3.cpp:28-31): info[4*j+{0,1,2,3}] = {z0, z1, is_binary, slot among
+// the binary columns}, info[4p] = number of binary columns (also returned on the host; synchronises the stream).
+// info needs 4p+1 doubles.
+int column_binary_info(bk_ctx* ctx, const double* X, long long ldx, int n, int p, double* info, int* nbin_host);
+// W = [1, c, {x_j or b1_j}, {x_j*c or b1_j*c}, {b0_s}, {b0_s*c}]  (n x (2p+2+2nbin)); for a binary column
+// b1_j = [x_j == z1_j], b0_s = [x_j == z0_j] (s = its slot)
+int build_kpass_rhs(bk_ctx* ctx, const double* X, long long ldx, int n, int p, int nbin, const double* c,
                     const double* info, double* W, long long ldw);
 // From KW = K W:  D (n x p, marginal effects in standardised units) and R (n x p, the vectors
 // whose V-quadratic form gives the variance), following src/bigderiv_v3.cpp:31-106 in the
 // reduced form of SURVEY.md A.5.
-int deriv_epilogue(bk_ctx* ctx, const double* X, long long ldx, int n, int p, const double* KW,
+int deriv_epilogue(bk_ctx* ctx, const double* X, long long ldx, int n, int p, int nbin, const double* KW,
                    long long ldkw, const double* info, double sigma, double* D, long long ldd,
                    double* R, long long ldr);
 // var[j] = factor_j * sum_i s[i] * G[i,j]^2 ; G = Q'R (k x p); factor from info/sigma/n;

@@ -10,9 +10,10 @@
 // Kernel 1: thread = row, CTA = 256 rows x one k-slice; the 2L weight columns of the slice
 //           are staged in shared memory (broadcast reads), Q is read coalesced along rows,
 //           2L FP64 FMAs per loaded element.  Partials go to a [ksplit][2L][rows] buffer.
-// Kernel 2: fixed-order reduction over the k-slices, (c/d)^2, per-CTA partial sums.
-// Kernel 3: fixed-order sum of the CTA partials -> Le[L].  Deterministic (no atomics), so the
-//           discrete decisions of the golden section are reproducible run to run.
+// Kernel 2: fixed-order reduction over the k-slices, (c/d)^2, per-CTA partial sums; the CTA that
+//           finishes last adds them in a fixed order -> Le[L].  Deterministic (the only atomic is
+//           the arrival counter), so the discrete decisions of the golden section are
+//           reproducible run to run.
 // Roofline: HBM, 8 n k bytes per pass.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -80,8 +81,10 @@ __global__ void __launch_bounds__(256)
 template <int L>
 __global__ void __launch_bounds__(256)
     loo_finish_kernel(const double* __restrict__ part, int n_rows, int ksplit,
-                      double* __restrict__ blockpart, double* __restrict__ coeffs) {
+                      double* __restrict__ blockpart, double* __restrict__ coeffs,
+                      unsigned* __restrict__ done, double* __restrict__ Le) {
   __shared__ double red[32];
+  __shared__ bool last;
   const int row = blockIdx.x * 256 + threadIdx.x;
   double e[L];
 #pragma unroll
@@ -105,16 +108,21 @@ __global__ void __launch_bounds__(256)
     const double s = block_sum(e[l], red);
     if (threadIdx.x == 0) blockpart[(size_t)blockIdx.x * L + l] = s;
   }
-}
-
-template <int L>
-__global__ void loo_final_kernel(const double* __restrict__ blockpart, int nblocks,
-                                 double* __restrict__ Le) {
-  const int l = threadIdx.x;
-  if (l >= L) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * L + l];
-  Le[l] = s;
+  // the CTA that finishes last adds the per-CTA sums in a FIXED order (deterministic: the golden section is a
+  // discrete decision path) - this used to be a third launch
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < L) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(blockpart + (size_t)b * L + threadIdx.x);
+    Le[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *done = 0u;  // ready for the next pass
 }
 
 template <int L>
@@ -132,9 +140,7 @@ static int loo_run(bk_ctx* ctx, const double* Q, long long ldq, int n_rows, int 
   dim3 grid(rb, ksplit);
   loo_partial_kernel<L><<<grid, 256, 0, ctx->stream>>>(Q, ldq, n_rows, k, ev, z, lp, ksplit, part);
   BK_LAUNCHED(ctx);
-  loo_finish_kernel<L><<<rb, 256, 0, ctx->stream>>>(part, n_rows, ksplit, bp, coeffs);
-  BK_LAUNCHED(ctx);
-  loo_final_kernel<L><<<1, 32, 0, ctx->stream>>>(bp, rb, Le_dev);
+  loo_finish_kernel<L><<<rb, 256, 0, ctx->stream>>>(part, n_rows, ksplit, bp, coeffs, ctx->counters.p, Le_dev);
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
   return BK_OK;

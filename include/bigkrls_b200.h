@@ -130,6 +130,7 @@ BK_API int bk_dgemm(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k
 /* Communicator for row-partitioned multi-GPU runs: one process per GPU.  All buffers are
  * DEVICE pointers on the calling rank's GPU; the callbacks must be complete (stream-
  * synchronised) when they return.  world == 1 -> every callback may be NULL. */
+typedef struct bk_peer bk_peer;   /* native peer-memory communicator (NVLink, CUDA IPC), see bk_peer_create */
 typedef struct bk_comm {
   int rank;
   int world;
@@ -141,21 +142,38 @@ typedef struct bk_comm {
   int (*allgatherv)(void* user, double* dev_buf, const int64_t* counts, const int64_t* displs);
   /* broadcast n doubles from `root` */
   int (*broadcast)(void* user, double* dev_buf, int64_t n, int root);
+  /* optional (may be NULL): when set, the fit does not use the callbacks above at all - every exchange is a
+   * kernel of the library storing into the other ranks' HBM over NVLink (no host synchronisation), the dense->band
+   * stage of the eigensolver is distributed over the ranks, and the block-Krylov path keeps K partitioned. */
+  bk_peer* peer;
 } bk_comm;
+
+/* Bootstrap for bk_peer_create: a HOST all-gather of `bytes` bytes per rank (recv holds world * bytes, in rank
+ * order) - torch.distributed.all_gather_object, MPI_Allgather, a socket ...  Called a handful of times when the
+ * communicator is created or its symmetric heap grows, never on the data path. */
+typedef int (*bk_exchange_fn)(void* user, const void* send, void* recv, int64_t bytes);
+/* Collective over all ranks (one process per GPU, at most 8, one node with NVLink peer access): every rank
+ * allocates a symmetric heap, the CUDA IPC handles travel through `exchange`, and every heap is mapped into every
+ * process. */
+BK_API int bk_peer_create(bk_ctx* ctx, int rank, int world, bk_exchange_fn exchange, void* user, bk_peer** out);
+BK_API void bk_peer_destroy(bk_peer* p);   /* collective */
+/* collective self-test of the peer collectives (all-reduce, all-gather-v, broadcast): *failures = mismatches */
+BK_API int bk_peer_selftest(bk_peer* p, int* failures);
 
 typedef struct bk_fit_opts {
   double sigma;            /* kernel bandwidth (R default: ncol(X)) */
   double eigtrunc;         /* keep eigenpairs with value >= eigtrunc * largest (R/bigKRLS_Rcpp_functions.R:190) */
   int64_t neig;            /* number of eigenpairs (n = full decomposition) */
   double lambda;           /* > 0: user lambda, skip the search; <= 0: golden-section search */
-  double L, U;             /* search bounds; <= 0 / <= 0: reference defaults (bounds loops) */
+  double L, U;             /* search bounds; L < 0 (or NaN) / U <= 0: not supplied -> the reference's bounds loops
+                              (a user L = 0 is legal, R/bigKRLS.R:225-228) */
   double tol;              /* <= 0: 1e-3 * n (what the reference always ends up using) */
   int derivative;          /* compute marginal effects */
   int vcov;                /* compute vcov.c / vcov.fitted */
   int n_which;             /* number of derivative columns; 0 = all */
   const int32_t* which;    /* 0-based column indices, n_which of them */
   double y_sd;             /* sd(y) of the un-standardised y: folded into vcov outputs (R/bigKRLS.R:439,446) */
-  int loo_batch;           /* lambda candidates evaluated per pass over Q (speculative tree), 1..15; 0 = default 7 */
+  int loo_batch;           /* lambda candidates evaluated per pass over Q (speculative tree), 1..15; 0 = default 15 */
   int keep_vcov_fitted;    /* 0: skip vcov.fitted (e.g. folds of a cross-validation) */
   double* K_host;          /* optional HOST destination for this rank's column block of K (n x (c1-c0), c0 = n*rank/world,
                               c1 = n*(rank+1)/world): the copy is queued on a second stream as soon as the kernel stage
@@ -223,6 +241,11 @@ BK_API int bk_fit_get_binary(const bk_fit* f, int32_t* host);         /* n_deriv
  * y_sd^2 units, before the Neffective correction) may be NULL. */
 BK_API int bk_fit_predict(const bk_fit* f, const double* newXs, int64_t m, double* pred_std,
                    double* Knew, double* se2);
+/* Same, and vcov_pred (m x m, may be NULL) = Knew vcov.est.c Knew' - the reference's `vcov.est.pred`
+ * (R/bigKRLS.R:605; y_sd^2 units, before the Neffective correction), formed spectrally as
+ * y_sd^2 sigmasq (Knew Q) diag((ev+lambda)^-2) (Knew Q)'. */
+BK_API int bk_fit_predict_full(const bk_fit* f, const double* newXs, int64_t m, double* pred_std,
+                        double* Knew, double* se2, double* vcov_pred);
 
 /* ---- test / measurement hooks ---------------------------------------------------------- */
 /* FP64 micro-benchmarks used to establish the roofline denominators (tools/):
@@ -234,7 +257,7 @@ BK_API int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double*
 BK_API int bk_dgemm_bench(bk_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, int lower, double beta,
                    int iters, double* seconds);
 
-/* Stage-level hooks of the eigensolver (tests/test_gpu_eigen_stages.py): tridiagonalisation only
+/* Stage-level hooks of the eigensolver (tests/test_gpu_ops.py, tests/test_gpu_twostage.py): tridiagonalisation only
  * (A n x n host -> d[n], e[n-1]) and divide & conquer only (d, e host -> evals ascending, Z n x n
  * eigenvectors of the tridiagonal, column c <-> c-th LARGEST; Z may be NULL). */
 /* general library GEMM on host buffers, C (in/out) = alpha op(A) op(B) + beta C, optional lower-tile mode */

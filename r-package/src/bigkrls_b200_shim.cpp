@@ -54,10 +54,10 @@ RcppExport SEXP _bigKRLS_BigSolveForc(SEXP pQ, SEXP ev, SEXP y, SEXP lambda) {
   BEGIN_RCPP
   NumericVector e(ev), yy(y);
   const int64_t n = nr(pQ), k = nc(pQ);
-  NumericVector coeffs(n);
+  NumericMatrix coeffs(n, 1);  // arma::colvec wraps to an n x 1 matrix (src/solveforc.cpp:60-64)
   double Le = 0;
   chk(bk_solve_for_c(ctx(), mat(pQ), n, k, e.begin(), yy.begin(), as<double>(lambda), &Le, coeffs.begin()));
-  return List::create(Le, coeffs);
+  return List::create(_["Le"] = Le, _["coeffs"] = coeffs);
   END_RCPP
 }
 // src/multdiag.cpp:26-37
@@ -112,6 +112,25 @@ RcppExport SEXP _bigKRLS_BigNeffective(SEXP pX) {
 }
 
 // ---- fused path: one .Call per fit, outputs written into caller-allocated big.matrix objects ---------
+// The device-resident fit is owned by an external pointer: freed by R's garbage collector (or on any error
+// path of the call that creates it), used again by _bigKRLS_predict.
+struct FitGuard {
+  bk_fit* f = nullptr;
+  ~FitGuard() {
+    if (f) bk_fit_free(f);
+  }
+  bk_fit* release() {
+    bk_fit* r = f;
+    f = nullptr;
+    return r;
+  }
+};
+static void fit_finalizer(SEXP xp) {
+  bk_fit* f = (bk_fit*)R_ExternalPtrAddr(xp);
+  if (f) bk_fit_free(f);
+  R_ClearExternalPtr(xp);
+}
+
 // Xs, ys standardised (R/bigKRLS.R:251-254); pK / pVc / pVf / pD are big.matrix addresses or R_NilValue.
 RcppExport SEXP _bigKRLS_fit(SEXP pXs, SEXP ys, SEXP sigma, SEXP Neig, SEXP eigtrunc, SEXP lambda, SEXP which,
                              SEXP derivative, SEXP vcov, SEXP ysd, SEXP pK, SEXP pVc, SEXP pVf, SEXP pD) {
@@ -133,24 +152,45 @@ RcppExport SEXP _bigKRLS_fit(SEXP pXs, SEXP ys, SEXP sigma, SEXP Neig, SEXP eigt
   o.which = w0.empty() ? nullptr : w0.data();
   o.y_sd = as<double>(ysd);
   if (!Rf_isNull(pK)) o.K_host = mat(pK);  // copied under the eigensolver; bk_fit_get_K below is then a no-op
-  bk_fit* f = nullptr;
-  chk(bk_fit_run(ctx(), mat(pXs), y.begin(), n, p, &o, nullptr, &f));
+  FitGuard g;  // chk() throws: the guard frees the device state on every error path below
+  chk(bk_fit_run(ctx(), mat(pXs), y.begin(), n, p, &o, nullptr, &g.f));
   bk_fit_info info;
-  bk_fit_get_info(f, &info);
-  NumericVector ev(info.neig), coeffs(n), yhat(n), var(info.n_deriv);
-  bk_fit_get_eigenvalues(f, ev.begin());
-  bk_fit_get_coeffs(f, coeffs.begin());
-  bk_fit_get_yfitted(f, yhat.begin());
-  if (!Rf_isNull(pK)) chk(bk_fit_get_K(f, mat(pK)));
-  if (o.vcov && !Rf_isNull(pVc)) chk(bk_fit_get_vcov_c(f, mat(pVc)));
-  if (o.vcov && !Rf_isNull(pVf)) chk(bk_fit_get_vcov_fitted(f, mat(pVf)));
+  chk(bk_fit_get_info(g.f, &info));
+  NumericVector ev(info.neig), yhat(n), var(info.n_deriv);
+  NumericMatrix coeffs(n, 1);
+  chk(bk_fit_get_eigenvalues(g.f, ev.begin()));
+  chk(bk_fit_get_coeffs(g.f, coeffs.begin()));
+  chk(bk_fit_get_yfitted(g.f, yhat.begin()));
+  if (!Rf_isNull(pK)) chk(bk_fit_get_K(g.f, mat(pK)));
+  if (o.vcov && !Rf_isNull(pVc)) chk(bk_fit_get_vcov_c(g.f, mat(pVc)));
+  if (o.vcov && !Rf_isNull(pVf)) chk(bk_fit_get_vcov_fitted(g.f, mat(pVf)));
   if (o.derivative && !Rf_isNull(pD)) {
-    chk(bk_fit_get_derivatives(f, mat(pD)));
-    chk(bk_fit_get_var_avgderiv(f, var.begin()));
+    chk(bk_fit_get_derivatives(g.f, mat(pD)));
+    chk(bk_fit_get_var_avgderiv(g.f, var.begin()));
   }
-  bk_fit_free(f);
-  return List::create(_["values"] = ev, _["lastkeeper"] = (double)info.lastkeeper, _["lambda"] = info.lambda,
-                      _["Le"] = info.Le, _["coeffs"] = coeffs, _["yfitted"] = yhat, _["varavgderiv"] = var);
+  SEXP handle = PROTECT(R_MakeExternalPtr(g.release(), R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(handle, fit_finalizer, TRUE);
+  List out = List::create(_["values"] = ev, _["lastkeeper"] = (double)info.lastkeeper, _["lambda"] = info.lambda,
+                          _["Le"] = info.Le, _["coeffs"] = coeffs, _["yfitted"] = yhat, _["varavgderiv"] = var,
+                          _["handle"] = handle);
+  UNPROTECT(1);
+  return out;
+  END_RCPP
+}
+
+// predict.bigKRLS on the device state of a fit (R/bigKRLS.R:596-613): newdata standardised with the training
+// mean/sd; pKnew (M x N) and pVcovPred (M x M) are caller-allocated big.matrix addresses or R_NilValue.
+// -> list(predicted (standardised units), se2 (diag of vcov.est.pred, before the Neffective correction))
+RcppExport SEXP _bigKRLS_predict(SEXP handle, SEXP pNew, SEXP pKnew, SEXP pVcovPred, SEXP sePred) {
+  BEGIN_RCPP
+  bk_fit* f = (bk_fit*)R_ExternalPtrAddr(handle);
+  if (!f) stop("bigKRLS fit handle was released; refit or use the per-op path");
+  const int64_t m = nr(pNew);
+  const bool se = as<bool>(sePred);
+  NumericVector pred(m), se2(se ? m : 0);
+  chk(bk_fit_predict_full(f, mat(pNew), m, pred.begin(), Rf_isNull(pKnew) ? nullptr : mat(pKnew),
+                          se ? se2.begin() : nullptr, (se && !Rf_isNull(pVcovPred)) ? mat(pVcovPred) : nullptr));
+  return List::create(_["predicted"] = pred, _["se2"] = se2);
   END_RCPP
 }
 
@@ -167,6 +207,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bigKRLS_BigSolveForc", (DL_FUNC)&_bigKRLS_BigSolveForc, 4},
     {"_bigKRLS_BigTempKernel", (DL_FUNC)&_bigKRLS_BigTempKernel, 4},
     {"_bigKRLS_fit", (DL_FUNC)&_bigKRLS_fit, 14},
+    {"_bigKRLS_predict", (DL_FUNC)&_bigKRLS_predict, 5},
     {NULL, NULL, 0}};
 
 RcppExport void R_init_bigKRLS(DllInfo* dll) {

@@ -25,7 +25,7 @@ def run_host_search(values, n, Q, ys, batch):
     lam, L, U = C.c_double(), C.c_double(), C.c_double()
     probes, passes = C.c_int(), C.c_int()
     ev = np.ascontiguousarray(values)
-    _lib.check(lib.bk_host_lambda_search(_lib.dptr(ev), len(ev), n, 0.0, 0.0, 0.0, batch,
+    _lib.check(lib.bk_host_lambda_search(_lib.dptr(ev), len(ev), n, -1.0, 0.0, 0.0, batch,
                                          C.cast(cbf, C.c_void_p), None, C.byref(lam), C.byref(L),
                                          C.byref(U), C.byref(probes), C.byref(passes)))
     return lam.value, L.value, U.value, probes.value, passes.value
@@ -117,7 +117,7 @@ def host_bounds(values, n):
     lam, L, U = C.c_double(), C.c_double(), C.c_double()
     probes, passes = C.c_int(), C.c_int()
     ev = np.ascontiguousarray(values, dtype=np.float64)
-    rc = lib.bk_host_lambda_search(_lib.dptr(ev), len(ev), n, 0.0, 0.0, 0.0, 7, C.cast(cbf, C.c_void_p), None,
+    rc = lib.bk_host_lambda_search(_lib.dptr(ev), len(ev), n, -1.0, 0.0, 0.0, 7, C.cast(cbf, C.c_void_p), None,
                                    C.byref(lam), C.byref(L), C.byref(U), C.byref(probes), C.byref(passes))
     return rc, L.value, U.value
 
