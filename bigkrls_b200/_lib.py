@@ -30,12 +30,13 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 ALLGATHERV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, c_int64_p, c_int64_p)
 BROADCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int)
 LE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_int, c_double_p)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class Comm(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p),
                 ("allreduce_sum", ALLREDUCE_FN), ("allgatherv", ALLGATHERV_FN),
-                ("broadcast", BROADCAST_FN)]
+                ("broadcast", BROADCAST_FN), ("peer", C.c_void_p)]
 
 
 class FitOpts(C.Structure):
@@ -102,6 +103,9 @@ _SIGNATURES = {
     "bk_neffective": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, c_double_p]),
     "bk_dgemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, c_double_p,
                            C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64]),
+    "bk_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, EXCHANGE_FN, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bk_peer_destroy": (None, [C.c_void_p]),
+    "bk_peer_selftest": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "bk_fit_default_opts": (None, [C.POINTER(FitOpts), C.c_int64, C.c_int64]),
     "bk_fit_run": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.POINTER(FitOpts),
                              C.POINTER(Comm), C.POINTER(C.c_void_p)]),

@@ -70,9 +70,16 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
     `which_derivatives` is 1-based like R.  `comm` is a bigkrls_b200.dist.TorchComm for
     multi-GPU (one process per GPU) runs.  The reference's quirk B.1 (derivative column i is
     divided by X.init.sd[i], not X.init.sd[which.derivatives[i]], R/bigKRLS.R:395-397) is
-    replicated unless fix_sd_index_bug=True.  `Ncores` is accepted and ignored (the PSOCK
-    column-parallelism of R/bigKRLS.R:332-363 is replaced by the GPU path)."""
+    replicated unless fix_sd_index_bug=True.  `Ncores` - in the reference the number of PSOCK worker processes of
+    the marginal-effects stage (R/bigKRLS.R:257,332-363) - selects how many GPUs (ranks of `comm`) take part in the
+    partitioned stages: the first Ncores ranks run the fit, the others return None; without `comm` there is one
+    GPU and Ncores has nothing to select."""
     lib = _lib.load()
+    sub_comm = None
+    if comm is not None and Ncores is not None and int(Ncores) < comm.world:
+        comm = sub_comm = comm.sub(int(Ncores))        # collective over all ranks of the parent communicator
+        if comm is None:
+            return None
     if X is None or y is None:
         _stop("y and X are required")
     X0 = np.asarray(X, dtype=np.float64)
@@ -167,6 +174,8 @@ def bigKRLS(y=None, X=None, sigma=None, derivative=True, which_derivatives=None,
         opts.K_host = K.ctypes.data
     check(lib.bk_fit_run(ctx.handle, dptr(Xs), dptr(ys), n, p, C.byref(opts), cptr, C.byref(h)))
     w._fit, w._ctx = h, ctx
+    if sub_comm is not None and getattr(sub_comm, "close", None):
+        sub_comm.close()                               # the fit's device state does not live in the peer heaps
     info = FitInfo()
     check(lib.bk_fit_get_info(h, C.byref(info)))
     w["_info"] = info.as_dict()

@@ -159,7 +159,10 @@ struct bk_ctx {
   int max_smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // high-priority stream for look-ahead work (panel factorisation under an update)
   bk::DevBuf<double> gemm_ws;          // split-K partials
+  bk::DevBuf<double> gemm_ws_side;     // the same for GEMMs issued on the side stream
+  std::vector<cudaEvent_t> event_pool; // timing / ordering events reused across fits (created on first use)
   bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
   bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
   bk::DevBuf<unsigned int> counters;   // 64 arrival counters, zero between kernels (last-CTA-done reductions)
@@ -268,6 +271,35 @@ void copier_destroy(HostCopier* c);
 int copier_submit(bk_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t after, CopyTicket* out);
 int copier_wait(CopyTicket* t);
 int copy_to_host(bk_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t after);
+
+// Work issued inside the scope goes to the side stream (with its own split-K workspace) instead of the main one.
+struct SideStreamScope {
+  bk_ctx* c;
+  cudaStream_t saved;
+  SideStreamScope(bk_ctx* ctx) : c(ctx), saved(ctx->stream) {
+    c->stream = c->side_stream;
+    std::swap(c->gemm_ws.p, c->gemm_ws_side.p);
+    std::swap(c->gemm_ws.n, c->gemm_ws_side.n);
+    std::swap(c->gemm_ws.pooled, c->gemm_ws_side.pooled);
+    std::swap(c->gemm_ws.pool_stream, c->gemm_ws_side.pool_stream);
+  }
+  ~SideStreamScope() {
+    c->stream = saved;
+    std::swap(c->gemm_ws.p, c->gemm_ws_side.p);
+    std::swap(c->gemm_ws.n, c->gemm_ws_side.n);
+    std::swap(c->gemm_ws.pooled, c->gemm_ws_side.pooled);
+    std::swap(c->gemm_ws.pool_stream, c->gemm_ws_side.pool_stream);
+  }
+};
+// i-th event of the context's pool (timing enabled), created on first use
+inline cudaEvent_t pool_event(bk_ctx* c, size_t i) {
+  while (c->event_pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    c->event_pool.push_back(e);
+  }
+  return c->event_pool[i];
+}
 
 // launch-count bookkeeping
 #define BK_LAUNCHED(ctx) ((ctx)->n_launches++)

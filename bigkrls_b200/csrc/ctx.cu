@@ -45,6 +45,11 @@ int bk_init(int device, bk_ctx** out) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   BK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   BK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    BK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    BK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
+  }
   if (bk::pool_enabled()) {
     // keep freed blocks cached in the device's default pool (trimmed again in bk_destroy)
     cudaMemPool_t pool;
@@ -68,6 +73,9 @@ void bk_destroy(bk_ctx* ctx) {
   bk::copier_destroy(ctx->copier);
   ctx->copier = nullptr;
   ctx->gemm_ws.release();
+  ctx->gemm_ws_side.release();
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  ctx->event_pool.clear();
   ctx->barrier.release();
   ctx->scratch.release();
   ctx->counters.release();
@@ -80,6 +88,7 @@ void bk_destroy(bk_ctx* ctx) {
   if (bk::alloc_stream() == ctx->stream) bk::alloc_stream() = nullptr;
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->side_stream);
   delete ctx;
 }
 
@@ -89,6 +98,7 @@ int bk_trim(bk_ctx* ctx) {
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   for (auto& w : ctx->ws) w.release();
   ctx->gemm_ws.release();
+  ctx->gemm_ws_side.release();
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (bk::pool_enabled()) {
     cudaMemPool_t pool;

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+struct bk_peer;
+
 namespace bk {
 
 // A (n x n, lower triangle referenced and overwritten) -> d[n], e[n-1], tau[n-1] (device);
@@ -76,6 +78,18 @@ struct TwoStage {
 // K (n x n, only read) -> d, e (device, length n); reflectors kept in ts for twostage_back
 int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage* ts, double* d, double* e);
 int twostage_back(bk_ctx* ctx, TwoStage* ts, double* Z, long long ldz, int k);
+// Distributed stage 1 (sy2sb.cu, peer.cuh): the trailing matrix lives block-cyclically on the ranks of `peer`, built
+// straight from X (n x p standardised data, Gaussian kernel with bandwidth sigma).  Collective.
+size_t sy2sb_dist_heap_bytes(int n);
+int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n, double* Afact,
+               double* Tstore, double* AB, int ldab, DevBuf<double>& aloc_cache, BandStats* stats);
+int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
+                         TwoStage* ts, double* d, double* e);
+// Collective full eigensolver on the kernel matrix of X: stage 1 on all ranks, the rest on rank 0.  Only rank 0
+// fills evals_host / n_want / Z; the caller broadcasts.
+int eigen_full_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
+                    double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
+                    EigenTimes* times);
 static constexpr int kTwoStageFullMax = 16384;  // largest n for which the two-stage path is taken for ALL vectors
 bool use_twostage(int n, int max_want, double rel_thresh);
 inline long long sytrd_ld(int n) { return ((long long)n + 15) / 16 * 16; }
@@ -86,8 +100,11 @@ struct TopkStats {
   int restarts = 0, matvecs = 0, block = 0, basis = 0;
   double residual = 0;
 };
+// With `peer`: K is this rank's column block K[:, c0:c0+nloc] and the K X products are distributed (collective, every
+// rank returns the same values and vectors).
+size_t eigen_topk_heap_bytes(int n);
 int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
-               long long ldz, TopkStats* stats);
+               long long ldz, TopkStats* stats, bk_peer* peer = nullptr, int c0 = 0, int nloc = 0);
 // policy shared by bk_eigen and the fused fit
 inline bool use_topk(long long n, long long neig) { return n >= 512 && neig * 3 <= n; }
 

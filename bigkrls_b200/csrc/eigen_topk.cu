@@ -18,6 +18,7 @@
 #include "dgemm.cuh"
 #include "eigen.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace bk {
 
@@ -112,9 +113,33 @@ int project_out(Ws& w, const double* V, int m, double* W, int b) {
 
 }  // namespace
 
+size_t eigen_topk_heap_bytes(int n) { return sizeof(double) * 2 * (size_t)n * 128 + 4096; }
+
 int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
-               long long ldz, TopkStats* stats) {
+               long long ldz, TopkStats* stats, bk_peer* peer, int c0, int nloc) {
   BK_REQUIRE(k >= 1 && k <= n, "eigen_topk: k must be in 1..n");
+  // K X.  Single GPU: one GEMM over the whole K.  With a peer communicator K stays PARTITIONED: `K` is this rank's
+  // column block K[:, c0:c0+nloc] (= its row panel, K is symmetric), the rank forms its rows of K X and stores them
+  // into every other rank's copy of the block over NVLink (one all-gather of n x b per product); the rest of the
+  // iteration (orthogonalisation, Rayleigh-Ritz) is replicated and bit-identical on every rank.
+  size_t y_off[2] = {0, 0};
+  unsigned mv_count = 0;
+  if (peer) {
+    for (int q = 0; q < 2; ++q) BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * 128, &y_off[q]));
+    BK_TRY(peer_barrier(peer, ctx->stream));
+  }
+  auto matvec = [&](const double* X, int bx, double* KX) -> int {
+    if (!peer) return gemm(ctx, false, false, n, bx, n, 1.0, K, ldk, X, n, 0.0, KX, n);
+    const int q = (int)(mv_count++ & 1u);
+    double* Y = peer_ptr(peer, y_off[q]);
+    const unsigned others = ((1u << peer->world) - 1u) & ~(1u << peer->rank);
+    BK_TRY(gemm(ctx, true, false, nloc, bx, n, 1.0, K, ldk, X, n, 0.0, Y + c0, n));
+    const unsigned seq = peer_next_seq(peer, CH_KRYLOV);
+    BK_TRY(peer_push2d(peer, Y + c0, n, nloc, bx, y_off[q] + sizeof(double) * (size_t)c0, n, others, CH_KRYLOV, seq,
+                       ctx->stream));
+    BK_TRY(peer_wait(peer, CH_KRYLOV, others, seq, ctx->stream));
+    return copy_matrix(ctx, Y, n, n, bx, 1.0, KX, n);
+  };
   const int b = std::min(128, std::max(8, std::min(n, (k + 3) / 4)));
   const int m_max = std::min(n, k + 8 * b);
   const double tol = 2e-13;
@@ -149,7 +174,7 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
     while (bx > 0 && m + bx <= m_max) {
       double* X = V.p + (size_t)m * n;
       double* KX = KV.p + (size_t)m * n;
-      BK_TRY(gemm(ctx, false, false, n, bx, n, 1.0, K, ldk, X, n, 0.0, KX, n));
+      BK_TRY(matvec(X, bx, KX));
       matvecs += bx;
       m += bx;
       BK_TRY(copy_matrix(ctx, KX, n, n, bx, 1.0, Wt.p, n));
@@ -211,6 +236,10 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
   for (int j = 0; j < k; ++j) evals_host[j] = th[j];
   if (Z) BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, Z, ldz));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (peer) {
+    BK_TRY(peer_barrier(peer, ctx->stream));
+    BK_TRY(peer_check(peer, ctx->stream));
+  }
   if (stats) {
     stats->restarts = outer + 1;
     stats->matvecs = matvecs;

@@ -25,6 +25,7 @@
 #include "dgemm.cuh"
 #include "eigen.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 using namespace bk;
 
@@ -43,6 +44,8 @@ struct bk_fit {
   bool have_vcov = false, have_vf = false, have_deriv = false;
   const double* K_host_done = nullptr;  // host buffer that already holds K (early D2H under the eigensolver)
   bk::CopyTicket k_copy;
+  bool k_block_only = false;  // K holds only the own column block (native multi-GPU fits), not the whole matrix
+  const double* kblock() const { return k_block_only ? K.p : K.p + (long long)c0 * n; }
   ~bk_fit() { bk::copier_wait(&k_copy); }  // K must outlive the queued copy
 };
 
@@ -288,42 +291,87 @@ int lambda_search(LooEvaluator& ev, double L, double U, double tol, double* lam_
   return BK_OK;
 }
 
+// sizes of the per-rank segments of an n-long (times `width`) field partitioned like the column blocks
+void block_partition(int n, int world, long long width, std::vector<long long>& counts, std::vector<long long>& displs) {
+  counts.resize(world);
+  displs.resize(world);
+  for (int r = 0; r < world; ++r) {
+    const long long a = (long long)n * r / world, b = (long long)n * (r + 1) / world;
+    counts[r] = (b - a) * width;
+    displs[r] = a * width;
+  }
+}
+
 int run_fit(bk_fit* f, const bk_comm* comm) {
   bk_ctx* ctx = f->ctx;
   const int n = f->n, p = f->p;
   const bk_fit_opts& o = f->opts;
   const long long ld = n;
   const bool multi = comm && comm->world > 1;
+  // native: every exchange is a kernel of this library storing into the peers' HBM (peer.cu); otherwise the
+  // host-provided callbacks (generic path: gloo on CPU boxes, any other transport)
+  bk_peer* peer = (multi && comm->peer) ? comm->peer : nullptr;
+  const bool native = peer != nullptr;
+  const int world = multi ? comm->world : 1, rank = multi ? comm->rank : 0;
   Timer tm, total;
   BK_TRY(tm.init(ctx->stream));
   BK_TRY(total.init(ctx->stream));
-  total.start();
   memset(&f->info, 0, sizeof(f->info));
   const uint64_t launches0 = ctx->n_launches;
+  const int nloc = f->c1 - f->c0;
+  const int pd_all = o.derivative ? f->pd : 0;
+  const bool topk = use_topk(n, f->neig);
+  const bool dist_eig = native && !topk && use_twostage(n, f->neig, o.eigtrunc);
+
+  size_t off_pack = 0, off_Q = 0, off_yhat = 0, off_D = 0;
+  if (native) {
+    BK_REQUIRE(peer->world == world && peer->rank == rank, "bk_fit_run: bk_comm and its peer communicator disagree");
+    // symmetric heap for this fit (collective; grows once, then reused): eigenvalue pack, Q for the broadcast from
+    // rank 0, gathered yhat and derivatives, and the buffers of the distributed eigensolver stages
+    size_t need = sizeof(double) * ((size_t)f->neig + 16 + (size_t)n * (topk ? 0 : f->neig) + (size_t)n +
+                                    (size_t)n * std::max(1, pd_all)) + 8192;
+    need += dist_eig ? sy2sb_dist_heap_bytes(n) : 0;
+    need += topk ? eigen_topk_heap_bytes(n) : 0;
+    BK_TRY(peer_ensure_heap(peer, need));
+    BK_TRY(peer_alloc(peer, sizeof(double) * ((size_t)f->neig + 16), &off_pack));
+    if (!topk) BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * f->neig, &off_Q));
+    BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n, &off_yhat));
+    BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * std::max(1, pd_all), &off_D));
+    // the previous fit is over on every rank before anybody stores into these buffers again
+    BK_TRY(peer_barrier(peer, ctx->stream));
+  }
+  total.start();
 
   // ---- 1/5 kernel -------------------------------------------------------------------------
   tm.start();
-  BK_TRY(f->K.alloc((size_t)n * n));
   if (!multi) {
+    BK_TRY(f->K.alloc((size_t)n * n));
     BK_TRY(gauss_kernel_sym(ctx, f->X.p, ld, n, p, o.sigma, f->K.p, ld));
+  } else if (native) {
+    // own column block only: nobody needs the whole kernel matrix (the eigensolver stages build their own columns
+    // straight from X, the K-pass and the D2H of K use the own block) - no exchange at all
+    BK_TRY(f->K.alloc((size_t)n * std::max(1, nloc)));
+    f->k_block_only = true;
+    BK_TRY(gauss_kernel_rect(ctx, f->X.p, ld, n, f->X.p + f->c0, ld, nloc, p, o.sigma, f->K.p, ld));
   } else {
     // own column block K[:, c0:c1] = kernel(X, X[c0:c1, :]) then in-place all-gather
-    BK_TRY(gauss_kernel_rect(ctx, f->X.p, ld, n, f->X.p + f->c0, ld, f->c1 - f->c0, p, o.sigma,
+    BK_TRY(f->K.alloc((size_t)n * n));
+    BK_TRY(gauss_kernel_rect(ctx, f->X.p, ld, n, f->X.p + f->c0, ld, nloc, p, o.sigma,
                              f->K.p + (long long)f->c0 * ld, ld));
-    std::vector<int64_t> counts(comm->world), displs(comm->world);
-    for (int r = 0; r < comm->world; ++r) {
-      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
+    std::vector<int64_t> counts(world), displs(world);
+    for (int r = 0; r < world; ++r) {
+      const int64_t a = (int64_t)n * r / world, b = (int64_t)n * (r + 1) / world;
       counts[r] = (b - a) * n;
       displs[r] = a * n;
     }
     COMM_CALL(comm->allgatherv(comm->user, f->K.p, counts.data(), displs.data()), "allgatherv(K)");
   }
+  const double* Kblk = f->kblock();  // K[:, c0:c1], ld n
   f->info.t_kernel = tm.stop();
   if (o.K_host) {
     // K is final: send this rank's column block to the host now, under the eigensolver (pinned destination: one
     // DMA on the copy stream; pageable big.matrix memory: the copy engine's bounce lanes, hostcopy.cu)
-    BK_TRY(copier_submit(ctx, o.K_host, f->K.p + (long long)f->c0 * ld, sizeof(double) * (size_t)n * (f->c1 - f->c0),
-                         ctx->stream, &f->k_copy));
+    BK_TRY(copier_submit(ctx, o.K_host, Kblk, sizeof(double) * (size_t)n * nloc, ctx->stream, &f->k_copy));
   }
 
   // ---- 2/5 eigen ----------------------------------------------------------------------------
@@ -333,56 +381,100 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   {
     DevBuf<double> Zfull;
     BK_TRY(Zfull.alloc((size_t)n * f->neig));
-    if (!multi || comm->rank == 0) {
-      std::vector<double> ev(n);
-      EigenTimes et;
-      if (use_topk(n, f->neig)) {
+    std::vector<double> ev(n);
+    EigenTimes et;
+    int eig_rc = BK_OK;
+    bool replicated = false;  // every rank already holds the result (no broadcast)
+    if (native && topk) {
+      // Neig << N: block Krylov with K partitioned over the ranks (one all-gather of n x b per K X)
+      TopkStats ts;
+      BK_TRY(eigen_topk(ctx, Kblk, ld, n, f->neig, ev.data(), Zfull.p, ld, &ts, peer, f->c0, nloc));
+      for (int i = 0; i < f->neig; ++i)
+        if (ev[i] >= o.eigtrunc * ev[0]) k = i + 1;
+      f->info.krylov_matvecs = ts.matvecs;
+      f->info.krylov_restarts = ts.restarts;
+      replicated = true;
+    } else if (dist_eig) {
+      // dense -> band distributed over all ranks, band -> tridiagonal, D&C and back-transformation on rank 0
+      eig_rc = eigen_full_dist(ctx, peer, f->X.p, ld, p, o.sigma, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et);
+      if (eig_rc == BK_ERR_CUDA || eig_rc == BK_ERR_COMM) return eig_rc;
+    } else if (!multi || rank == 0) {
+      DevBuf<double> Kfull;
+      const double* Kmat = f->K.p;
+      if (native) {
+        // single-GPU eigensolver path (small n, or all eigenvectors of a large matrix): rank 0 builds the whole
+        // kernel matrix itself - cheaper than gathering it
+        BK_TRY(Kfull.alloc((size_t)n * n));
+        BK_TRY(gauss_kernel_sym(ctx, f->X.p, ld, n, p, o.sigma, Kfull.p, ld));
+        Kmat = Kfull.p;
+      }
+      if (topk) {
         // Neig << N (reference: sp_mat + eigs_sym, src/eigen.cpp:18-22): restarted block Krylov
         TopkStats ts;
-        BK_TRY(eigen_topk(ctx, f->K.p, ld, n, f->neig, ev.data(), Zfull.p, ld, &ts));
+        eig_rc = eigen_topk(ctx, Kmat, ld, n, f->neig, ev.data(), Zfull.p, ld, &ts);
         k = 0;  // lastkeeper over the Neig values (R/bigKRLS_Rcpp_functions.R:190)
-        for (int i = 0; i < f->neig; ++i)
+        for (int i = 0; i < f->neig && eig_rc == BK_OK; ++i)
           if (ev[i] >= o.eigtrunc * ev[0]) k = i + 1;
         f->info.krylov_matvecs = ts.matvecs;
         f->info.krylov_restarts = ts.restarts;
       } else {
-        BK_TRY(eigen_full(ctx, f->K.p, ld, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et));
+        eig_rc = eigen_full(ctx, Kmat, ld, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et);
       }
-      for (int i = 0; i < f->neig; ++i) f->evals[i] = ev[i];
-      f->info.t_tridiag = et.tridiag;
-      f->info.t_dc = et.dc;
-      f->info.t_backtransform = et.backtransform;
-      f->info.sytrd_launches = et.sytrd.launches;
-      f->info.sytrd_kernel_seconds = et.sytrd.kernel_seconds;
-      f->info.sytrd_bytes = et.sytrd.algorithmic_bytes;
-      f->info.twostage = et.twostage;
-      f->info.t_sy2sb = et.t_sy2sb;
-      f->info.t_sb2st = et.t_sb2st;
-      f->info.t_q2 = et.t_q2;
-      f->info.t_q1 = et.t_q1;
-      f->info.band_gemm_launches = et.band.gemm_launches;
-      f->info.band_gemm_seconds = et.band.gemm_seconds;
-      f->info.band_gemm_flops = et.band.gemm_flops;
-      f->info.dc_levels = et.dc_stats.levels;
-      f->info.dc_merge_flops = (double)et.dc_stats.merge_flops;
-      f->info.dc_top_n = et.dc_stats.top_n;
-      f->info.dc_top_k = et.dc_stats.top_k;
+      if (!multi) BK_TRY(eig_rc);
+      if (eig_rc == BK_ERR_CUDA) return eig_rc;
     }
+    for (int i = 0; i < f->neig; ++i) f->evals[i] = ev[i];
+    f->info.t_tridiag = et.tridiag;
+    f->info.t_dc = et.dc;
+    f->info.t_backtransform = et.backtransform;
+    f->info.sytrd_launches = et.sytrd.launches;
+    f->info.sytrd_kernel_seconds = et.sytrd.kernel_seconds;
+    f->info.sytrd_bytes = et.sytrd.algorithmic_bytes;
+    f->info.twostage = et.twostage;
+    f->info.t_sy2sb = et.t_sy2sb;
+    f->info.t_sb2st = et.t_sb2st;
+    f->info.t_q2 = et.t_q2;
+    f->info.t_q1 = et.t_q1;
+    f->info.band_gemm_launches = et.band.gemm_launches;
+    f->info.band_gemm_seconds = et.band.gemm_seconds;
+    f->info.band_gemm_flops = et.band.gemm_flops;
+    f->info.dc_levels = et.dc_stats.levels;
+    f->info.dc_merge_flops = (double)et.dc_stats.merge_flops;
+    f->info.dc_top_n = et.dc_stats.top_n;
+    f->info.dc_top_k = et.dc_stats.top_k;
     BK_TRY(f->ev.alloc(f->neig + 1));
-    if (multi) {
-      // broadcast [k, evals] then Q[:, :k]
+    if (multi && !replicated) {
+      // broadcast [status | k, evals] then Q[:, :k].  Rank 0's status travels with the data: a numerical failure of
+      // the eigensolver there must not leave the other ranks waiting in a collective (they all return the error).
       std::vector<double> pack(f->neig + 1);
-      pack[0] = (double)k;
+      pack[0] = (eig_rc != BK_OK) ? (double)eig_rc : (double)k;
       for (int i = 0; i < f->neig; ++i) pack[1 + i] = f->evals[i];
-      BK_CUDA(cudaMemcpyAsync(f->ev.p, pack.data(), sizeof(double) * (f->neig + 1),
-                              cudaMemcpyHostToDevice, ctx->stream));
-      COMM_CALL(comm->broadcast(comm->user, f->ev.p, f->neig + 1, 0), "broadcast(evals)");
-      BK_CUDA(cudaMemcpyAsync(pack.data(), f->ev.p, sizeof(double) * (f->neig + 1),
-                              cudaMemcpyDeviceToHost, ctx->stream));
+      double* dpack = native ? peer_ptr(peer, off_pack) : f->ev.p;
+      if (rank == 0)
+        BK_CUDA(cudaMemcpyAsync(dpack, pack.data(), sizeof(double) * (f->neig + 1), cudaMemcpyHostToDevice, ctx->stream));
+      if (native)
+        BK_TRY(peer_broadcast_sym(peer, off_pack, f->neig + 1, 0, ctx->stream));
+      else
+        COMM_CALL(comm->broadcast(comm->user, dpack, f->neig + 1, 0), "broadcast(evals)");
+      BK_CUDA(cudaMemcpyAsync(pack.data(), dpack, sizeof(double) * (f->neig + 1), cudaMemcpyDeviceToHost, ctx->stream));
       BK_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (native) BK_TRY(peer_check(peer, ctx->stream));
+      if (pack[0] < 0.0) {
+        if (rank != 0) set_error("the eigensolver failed on rank 0 (status %d)", (int)pack[0]);
+        return (int)pack[0];
+      }
       k = (int)pack[0];
       for (int i = 0; i < f->neig; ++i) f->evals[i] = pack[1 + i];
-      COMM_CALL(comm->broadcast(comm->user, Zfull.p, (int64_t)n * k, 0), "broadcast(Q)");
+      if (native) {
+        double* Qs = peer_ptr(peer, off_Q);
+        if (rank == 0)
+          BK_CUDA(cudaMemcpyAsync(Qs, Zfull.p, sizeof(double) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        BK_TRY(peer_broadcast_sym(peer, off_Q, (long long)n * k, 0, ctx->stream));
+        if (rank != 0)
+          BK_CUDA(cudaMemcpyAsync(Zfull.p, Qs, sizeof(double) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        COMM_CALL(comm->broadcast(comm->user, Zfull.p, (int64_t)n * k, 0), "broadcast(Q)");
+      }
     }
     BK_REQUIRE(k >= 1, "eigen: no eigenpair retained");
     BK_CUDA(cudaMemcpyAsync(f->ev.p, f->evals.data(), sizeof(double) * f->neig, cudaMemcpyHostToDevice,
@@ -396,6 +488,8 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     } else {
       std::swap(f->Q.p, Zfull.p);
       std::swap(f->Q.n, Zfull.n);
+      std::swap(f->Q.pooled, Zfull.pooled);
+      std::swap(f->Q.pool_stream, Zfull.pool_stream);
     }
   }
   f->k = k;
@@ -414,7 +508,6 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   BK_TRY(z.alloc(k));
   BK_TRY(Le_dev.alloc(16));
   BK_TRY(gemm(ctx, true, false, k, 1, n, 1.0, f->Q.p, ld, f->y.p, ld, 0.0, z.p, k));
-  const int nloc = f->c1 - f->c0;
   double lam = o.lambda;
   if (!(lam > 0.0)) {
     double L = o.L, U = o.U;
@@ -425,7 +518,10 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     le.eval_batch = [&](const std::vector<double>& lams, double* out) -> int {
       BK_TRY(loo_batch(ctx, Qpanel, ld, nloc, k, f->ev.p, z.p, lams.data(), (int)lams.size(),
                        Le_dev.p, nullptr));
-      if (multi) COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
+      if (native)
+        BK_TRY(peer_allreduce_sum(peer, Le_dev.p, 16, ctx->stream));
+      else if (multi)
+        COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
       BK_CUDA(cudaMemcpyAsync(out, Le_dev.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
       BK_CUDA(cudaStreamSynchronize(ctx->stream));
       return BK_OK;
@@ -445,21 +541,23 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   // ---- 4/5 coefficients, fitted values ----------------------------------------------------------
   tm.start();
   BK_TRY(f->c.alloc(n));
-  BK_TRY(loo_batch(ctx, f->Q.p + f->c0, ld, nloc, k, f->ev.p, z.p, &lam, 1, Le_dev.p, f->c.p + f->c0));
-  if (multi) {
-    COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
-    std::vector<int64_t> counts(comm->world), displs(comm->world);
-    for (int r = 0; r < comm->world; ++r) {
-      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
-      counts[r] = b - a;
-      displs[r] = a;
+  std::vector<long long> cnt1, dsp1;
+  block_partition(n, world, 1, cnt1, dsp1);
+  if (native) {
+    // every rank holds all of Q: the n coefficients and Le are formed redundantly, nothing to exchange
+    BK_TRY(loo_batch(ctx, f->Q.p, ld, n, k, f->ev.p, z.p, &lam, 1, Le_dev.p, f->c.p));
+  } else {
+    BK_TRY(loo_batch(ctx, f->Q.p + f->c0, ld, nloc, k, f->ev.p, z.p, &lam, 1, Le_dev.p, f->c.p + f->c0));
+    if (multi) {
+      COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
+      std::vector<int64_t> counts(cnt1.begin(), cnt1.end()), displs(dsp1.begin(), dsp1.end());
+      COMM_CALL(comm->allgatherv(comm->user, f->c.p, counts.data(), displs.data()), "allgatherv(coeffs)");
     }
-    COMM_CALL(comm->allgatherv(comm->user, f->c.p, counts.data(), displs.data()), "allgatherv(coeffs)");
   }
   BK_CUDA(cudaMemcpyAsync(&f->Le, Le_dev.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 
-  // K-pass: KW = K [1 c {x_j|b_j} {x_j c|b_j c}] ; column 1 is yhat = K c  (R/bigKRLS.R:291)
-  const int pd = o.derivative ? f->pd : 0;
+  // K-pass: KW = K [1 c {x_j|b1_j} {x_j c|b1_j c} {b0} {b0 c}] ; column 1 is yhat = K c  (R/bigKRLS.R:291)
+  const int pd = pd_all;
   int nbin = 0;
   DevBuf<double> Xd, W, KW;
   BK_TRY(f->binfo.alloc(4 * std::max(1, pd) + 1));
@@ -480,18 +578,19 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   if (!multi)
     BK_TRY(gemm(ctx, false, false, n, mw, n, 1.0, f->K.p, ld, W.p, ld, 0.0, KW.p, ld));
   else
-    BK_TRY(gemm(ctx, true, false, nloc, mw, n, 1.0, f->K.p + (long long)f->c0 * ld, ld, W.p, ld, 0.0,
-                KW.p + f->c0, ld));
+    BK_TRY(gemm(ctx, true, false, nloc, mw, n, 1.0, Kblk, ld, W.p, ld, 0.0, KW.p + f->c0, ld));
   BK_TRY(f->yhat.alloc(n));
-  BK_TRY(copy_matrix(ctx, KW.p + f->c0 + ld, ld, nloc, 1, 1.0, f->yhat.p + f->c0, ld));
-  if (multi) {
-    std::vector<int64_t> counts(comm->world), displs(comm->world);
-    for (int r = 0; r < comm->world; ++r) {
-      const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
-      counts[r] = b - a;
-      displs[r] = a;
+  if (native) {
+    double* ys = peer_ptr(peer, off_yhat);
+    BK_TRY(copy_matrix(ctx, KW.p + f->c0 + ld, ld, nloc, 1, 1.0, ys + f->c0, ld));
+    BK_TRY(peer_allgatherv_sym(peer, off_yhat, cnt1.data(), dsp1.data(), ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(f->yhat.p, ys, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    BK_TRY(copy_matrix(ctx, KW.p + f->c0 + ld, ld, nloc, 1, 1.0, f->yhat.p + f->c0, ld));
+    if (multi) {
+      std::vector<int64_t> counts(cnt1.begin(), cnt1.end()), displs(dsp1.begin(), dsp1.end());
+      COMM_CALL(comm->allgatherv(comm->user, f->yhat.p, counts.data(), displs.data()), "allgatherv(yhat)");
     }
-    COMM_CALL(comm->allgatherv(comm->user, f->yhat.p, counts.data(), displs.data()), "allgatherv(yhat)");
   }
   BK_TRY(f->sig2.alloc(1));
   BK_TRY(residual_sigmasq(ctx, f->y.p, f->yhat.p, n, f->sig2.p));  // R/bigKRLS.R:294
@@ -548,23 +647,31 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     // G = Q' R (k x pd); r'V r = sigmasq * sum_i w2_i G_i^2
     BK_TRY(gemm(ctx, true, false, k, pd, nloc, 1.0, f->Q.p + f->c0, ld, R.p + f->c0, ld, 0.0, G.p, k));
     if (multi) {
-      COMM_CALL(comm->allreduce_sum(comm->user, G.p, (int64_t)k * pd), "allreduce(Q'R)");
-      // derivatives: gather row panels (n x pd is column-major, so go through a packed buffer)
-      DevBuf<double> pack;
-      BK_TRY(pack.alloc((size_t)n * pd));
-      std::vector<int64_t> counts(comm->world), displs(comm->world);
-      for (int r = 0; r < comm->world; ++r) {
-        const int64_t a = (int64_t)n * r / comm->world, b = (int64_t)n * (r + 1) / comm->world;
-        counts[r] = (b - a) * pd;
-        displs[r] = a * pd;
+      std::vector<long long> cntD, dspD;
+      block_partition(n, world, pd, cntD, dspD);
+      if (native) {
+        BK_TRY(peer_allreduce_sum(peer, G.p, (long long)k * pd, ctx->stream));
+        // derivatives: row panels through a packed symmetric buffer (n x pd is column-major)
+        double* pack = peer_ptr(peer, off_D);
+        BK_TRY(copy_matrix(ctx, f->D.p + f->c0, ld, nloc, pd, 1.0, pack + dspD[rank], nloc));
+        BK_TRY(peer_allgatherv_sym(peer, off_D, cntD.data(), dspD.data(), ctx->stream));
+        for (int r = 0; r < world; ++r) {
+          const int a = (int)((int64_t)n * r / world), b = (int)((int64_t)n * (r + 1) / world);
+          if (r != rank) BK_TRY(copy_matrix(ctx, pack + dspD[r], b - a, b - a, pd, 1.0, f->D.p + a, ld));
+        }
+      } else {
+        COMM_CALL(comm->allreduce_sum(comm->user, G.p, (int64_t)k * pd), "allreduce(Q'R)");
+        DevBuf<double> pack;
+        BK_TRY(pack.alloc((size_t)n * pd));
+        std::vector<int64_t> counts(cntD.begin(), cntD.end()), displs(dspD.begin(), dspD.end());
+        BK_TRY(copy_matrix(ctx, f->D.p + f->c0, ld, nloc, pd, 1.0, pack.p + displs[rank], nloc));
+        COMM_CALL(comm->allgatherv(comm->user, pack.p, counts.data(), displs.data()), "allgatherv(D)");
+        for (int r = 0; r < world; ++r) {
+          const int a = (int)((int64_t)n * r / world), b = (int)((int64_t)n * (r + 1) / world);
+          BK_TRY(copy_matrix(ctx, pack.p + displs[r], b - a, b - a, pd, 1.0, f->D.p + a, ld));
+        }
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));
       }
-      BK_TRY(copy_matrix(ctx, f->D.p + f->c0, ld, nloc, pd, 1.0, pack.p + displs[comm->rank], nloc));
-      COMM_CALL(comm->allgatherv(comm->user, pack.p, counts.data(), displs.data()), "allgatherv(D)");
-      for (int r = 0; r < comm->world; ++r) {
-        const int a = (int)((int64_t)n * r / comm->world), b = (int)((int64_t)n * (r + 1) / comm->world);
-        BK_TRY(copy_matrix(ctx, pack.p + displs[r], b - a, b - a, pd, 1.0, f->D.p + a, ld));
-      }
-      BK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     BK_TRY(deriv_variance_spectral(ctx, G.p, k, k, pd, w2.p, f->sig2.p, f->binfo.p, o.sigma, n, f->var.p));
     f->have_deriv = true;
@@ -572,6 +679,11 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   }
   BK_CUDA(cudaMemcpyAsync(&f->sigmasq, f->sig2.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (native) {
+    // every rank is through with the symmetric buffers of this fit; a timed-out wait surfaces here
+    BK_TRY(peer_barrier(peer, ctx->stream));
+    BK_TRY(peer_check(peer, ctx->stream));
+  }
   f->info.t_deriv = tm.stop();
   if (o.K_host) {
     BK_TRY(copier_wait(&f->k_copy));
@@ -608,7 +720,7 @@ int create_fit(bk_ctx* ctx, const double* Xs, const double* ys, bool on_device, 
   for (int i = 0; i < opts->n_which; ++i)
     BK_REQUIRE(opts->which && opts->which[i] >= 0 && opts->which[i] < p,
                "which.derivatives out of range");
-  if (comm && comm->world > 1)
+  if (comm && comm->world > 1 && !comm->peer)
     BK_REQUIRE(comm->allreduce_sum && comm->allgatherv && comm->broadcast,
                "bk_fit_run: communicator callbacks missing");
   BK_CUDA(bk::bind_ctx(ctx));
@@ -721,7 +833,7 @@ int bk_fit_col_range(const bk_fit* f, int64_t* c0, int64_t* c1) {
 int bk_fit_get_K(const bk_fit* f, double* host) {
   BK_REQUIRE(f && host, "bk_fit_get_K: NULL argument");
   if (host == f->K_host_done) return BK_OK;  // delivered during the fit (bk_fit_opts.K_host)
-  return get_vec(f, f->K.p + (long long)f->c0 * f->n, (size_t)f->n * (size_t)(f->c1 - f->c0), host);
+  return get_vec(f, f->kblock(), (size_t)f->n * (size_t)(f->c1 - f->c0), host);
 }
 int bk_fit_get_eigenvalues(const bk_fit* f, double* host) {
   BK_REQUIRE(f && host, "bk_fit_get_eigenvalues: NULL argument");

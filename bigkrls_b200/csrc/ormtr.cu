@@ -13,6 +13,7 @@
 #include "dgemm.cuh"
 #include "eigen.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace bk {
 
@@ -143,6 +144,58 @@ static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int 
     times->t_q2 = ts.t_q2;
     times->t_q1 = ts.t_q1;
     times->band = ts.band;
+  }
+  return BK_OK;
+}
+
+int eigen_full_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
+                    double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
+                    EigenTimes* times) {
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  DevBuf<double> d, e;
+  BK_TRY(d.alloc(n));
+  BK_TRY(e.alloc(n));
+  BK_CUDA(cudaMemsetAsync(e.p, 0, sizeof(double) * n, ctx->stream));
+  TwoStage ts;
+  tm.start();
+  BK_TRY(twostage_reduce_dist(ctx, peer, X, ldx, p, sigma, n, &ts, d.p, e.p));
+  const double t_tri = tm.stop();
+  if (times) {
+    times->tridiag = t_tri;
+    times->twostage = 1;
+    times->t_sy2sb = ts.t_sy2sb;
+    times->band = ts.band;
+  }
+  if (n_want) *n_want = 0;
+  if (peer->rank != 0) return BK_OK;
+  std::vector<double> dh(n), eh(n), ev(n);
+  BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(dh[i]) || !std::isfinite(eh[i])) {
+      set_error("eigen: tridiagonalisation produced a non-finite entry (NaN/Inf in the input?)");
+      return BK_ERR_NUMERIC;
+    }
+  tm.start();
+  int nw = 0;
+  StedcStats st;
+  BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
+  const double t_dc = tm.stop();
+  tm.start();
+  if (Z && nw > 0) BK_TRY(twostage_back(ctx, &ts, Z, ldz, nw));
+  const double t_bt = tm.stop();
+  for (int i = 0; i < n; ++i) evals_host[i] = ev[n - 1 - i];
+  if (n_want) *n_want = nw;
+  if (times) {
+    times->dc = t_dc;
+    times->backtransform = t_bt;
+    times->dc_stats = st;
+    times->sytrd = SytrdStats();
+    times->t_sb2st = ts.t_sb2st;
+    times->t_q2 = ts.t_q2;
+    times->t_q1 = ts.t_q1;
   }
   return BK_OK;
 }

@@ -90,10 +90,8 @@ __global__ void __launch_bounds__(256) peer_push1d_kernel(PeerDev pd, const doub
   peer_signal_last_cta(pd, peer_counter(pd, cnt_idx), gridDim.x, dst_mask, ch, seq);
 }
 
-int push1d(bk_peer* p, const double* src, long long n, size_t dst_off, unsigned dst_mask, int ch, cudaStream_t st,
-           unsigned* seq_out) {
-  const unsigned seq = peer_next_seq(p, ch);
-  if (seq_out) *seq_out = seq;
+int push1d(bk_peer* p, const double* src, long long n, size_t dst_off, unsigned dst_mask, int ch, unsigned seq,
+           cudaStream_t st) {
   const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(n, 1024), 4LL * p->ctx->sm_count));
   peer_push1d_kernel<<<blocks, 256, 0, st>>>(p->dev, src, n, dst_off, dst_mask, ch, seq, ch);
   BK_LAUNCHED(p->ctx);
@@ -211,9 +209,7 @@ int peer_allreduce_sum(bk_peer* p, double* buf, long long n, cudaStream_t st) {
 }
 
 int peer_push2d(bk_peer* p, const double* src, long long lds, int rows, int cols, size_t dst_off, long long ldd,
-                unsigned dst_mask, int ch, cudaStream_t st, unsigned* seq_out) {
-  const unsigned seq = peer_next_seq(p, ch);
-  if (seq_out) *seq_out = seq;
+                unsigned dst_mask, int ch, unsigned seq, cudaStream_t st) {
   const long long total = (long long)rows * cols;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(total, 512), 2LL * p->ctx->sm_count));
   peer_push2d_kernel<<<blocks, 256, 0, st>>>(p->dev, src, lds, rows, cols, dst_off, ldd, dst_mask, ch, seq, ch);
@@ -225,17 +221,18 @@ int peer_push2d(bk_peer* p, const double* src, long long lds, int rows, int cols
 int peer_allgatherv_sym(bk_peer* p, size_t off, const long long* counts, const long long* displs, cudaStream_t st) {
   const int me = p->rank;
   const unsigned others = ((1u << p->world) - 1u) & ~(1u << me);
-  unsigned seq = 0;
+  const unsigned seq = peer_next_seq(p, CH_GATHER);
   // my segment -> the same place in every other heap (a zero-length segment still signals)
   BK_TRY(push1d(p, peer_ptr(p, off) + displs[me], counts[me], off + sizeof(double) * (size_t)displs[me], others,
-                CH_GATHER, st, &seq));
+                CH_GATHER, seq, st));
   return peer_wait(p, CH_GATHER, others, seq, st);
 }
 
 int peer_broadcast_sym(bk_peer* p, size_t off, long long n, int root, cudaStream_t st) {
   const unsigned others = ((1u << p->world) - 1u) & ~(1u << root);
-  if (p->rank == root) return push1d(p, peer_ptr(p, off), n, off, others, CH_BCAST, st, nullptr);
-  return peer_wait(p, CH_BCAST, 1u << root, peer_next_seq(p, CH_BCAST), st);
+  const unsigned seq = peer_next_seq(p, CH_BCAST);  // every rank advances the channel
+  if (p->rank == root) return push1d(p, peer_ptr(p, off), n, off, others, CH_BCAST, seq, st);
+  return peer_wait(p, CH_BCAST, 1u << root, seq, st);
 }
 
 int peer_check(bk_peer* p, cudaStream_t st) {

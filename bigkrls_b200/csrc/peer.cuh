@@ -63,10 +63,11 @@ int peer_allreduce_sum(bk_peer* p, double* buf, long long n, cudaStream_t st);
 int peer_allgatherv_sym(bk_peer* p, size_t off, const long long* counts, const long long* displs, cudaStream_t st);
 // n doubles at heap offset `off` from `root` to everyone
 int peer_broadcast_sym(bk_peer* p, size_t off, long long n, int root, cudaStream_t st);
-// 2-D block copy into the heaps of the ranks in dst_mask (bit r; may include self) followed by a flag on `ch`;
-// returns the sequence number the receivers wait for.  src is any local device pointer.
+// 2-D block copy into the heaps of the ranks in dst_mask (bit r; may include self) followed by the flag `seq` on
+// channel `ch` (seq = peer_next_seq on EVERY rank, pushing or not, so that the channel counters stay equal).
+// src is any local device pointer.
 int peer_push2d(bk_peer* p, const double* src, long long lds, int rows, int cols, size_t dst_off, long long ldd,
-                unsigned dst_mask, int ch, cudaStream_t st, unsigned* seq_out);
+                unsigned dst_mask, int ch, unsigned seq, cudaStream_t st);
 // wait until the ranks in src_mask have signalled `seq` on channel `ch`
 int peer_wait(bk_peer* p, int ch, unsigned src_mask, unsigned seq, cudaStream_t st);
 // next sequence number of a channel (for kernels that signal themselves)

@@ -21,6 +21,7 @@
 #include "dgemm.cuh"
 #include "eigen.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace bk {
 
@@ -757,6 +758,32 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
   BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, ts->work.p, n));
   BK_TRY(sy2sb(ctx, ts->work.p, n, n, ts->Tstore.p, ts->AB.p, LDAB, &ts->band));
   ts->t_sy2sb = tm.stop();
+  BK_TRY(ts->VV.borrow(ctx->ws[1], (size_t)n * n));
+  tm.start();
+  BK_TRY(sb2st(ctx, ts->AB.p, n, d, e, ts->VV.p, ts->TAU.p, ts->maxhops));
+  ts->t_sb2st = tm.stop();
+  return BK_OK;
+}
+
+// Multi-GPU variant: stage 1 distributed over the ranks of `peer` (sy2sb_dist, straight from X - the kernel matrix is
+// never gathered); every rank ends with the complete factored matrix, rank 0 runs the band -> tridiagonal stage.
+int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
+                         TwoStage* ts, double* d, double* e) {
+  const int b = CB;
+  Timer tm;
+  BK_TRY(tm.init(ctx->stream));
+  ts->n = n;
+  ts->maxhops = n / b + 2;
+  const int npan = (int)ceil_div(n, b);
+  BK_TRY(ts->work.borrow(ctx->ws[0], (size_t)n * n));
+  BK_TRY(ts->AB.alloc((size_t)LDAB * n));
+  BK_TRY(ts->Tstore.alloc((size_t)npan * b * b));
+  tm.start();
+  BK_TRY(sy2sb_dist(ctx, peer, X, ldx, p, sigma, n, ts->work.p, ts->Tstore.p, ts->AB.p, LDAB, ctx->ws[2], &ts->band));
+  ts->t_sy2sb = tm.stop();
+  if (peer->rank != 0) return BK_OK;
+  BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
+  BK_CUDA(cudaMemsetAsync(ts->TAU.p, 0, sizeof(double) * (size_t)ts->maxhops * n, ctx->stream));
   BK_TRY(ts->VV.borrow(ctx->ws[1], (size_t)n * n));
   tm.start();
   BK_TRY(sb2st(ctx, ts->AB.p, n, d, e, ts->VV.p, ts->TAU.p, ts->maxhops));

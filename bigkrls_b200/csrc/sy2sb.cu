@@ -21,6 +21,7 @@
 #include "dgemm.cuh"
 #include "eigen.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace bk {
 
@@ -236,9 +237,153 @@ __global__ void extract_band_kernel(const double* __restrict__ A, long long lda,
   }
 }
 
+// Look-ahead variant: one panel at a time, and the factorisation of panel k+1 (cooperative QR kernel, V'V, T, V T -
+// all latency-bound) runs on the high-priority side stream UNDER the trailing update of panel k:
+//   main : Z_k = A22 (V T)_k -> W_k -> update of the NEXT panel's columns only -> [event] -> rest of the update
+//   side :                                                         [wait] QR_{k+1}, T_{k+1}, (V T)_{k+1} [event]
+// The update splits into the next panel's b columns (all rows) and the trailing (m-b) x (m-b) block (lower tiles,
+// mirrored); the mirror image of the panel columns is never read again.  [V W] / [W V] are double-buffered by
+// panel parity because QR_{k+1} writes V_{k+1} while the update still reads V_k, W_k.
+static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab,
+                           BandStats* stats) {
+  const int b = SB;
+  const int G = ctx->sm_count;
+  DevBuf<double> taus, part, prow, S, VT, S2, S3, PAbuf, PBbuf;
+  BK_TRY(taus.alloc(b));
+  BK_TRY(part.alloc((size_t)2 * G * b));
+  BK_TRY(prow.alloc(2 * b));
+  BK_TRY(S.alloc(b * b));
+  BK_TRY(VT.alloc((size_t)n * b));
+  BK_TRY(S2.alloc(b * b));
+  BK_TRY(S3.alloc(b * b));
+  BK_TRY(PAbuf.alloc((size_t)4 * b * n));
+  BK_TRY(PBbuf.alloc((size_t)4 * b * n));
+  BK_TRY(ctx->barrier.ensure(4));
+  BK_TRY(ctx->gemm_ws_side.ensure((size_t)4 << 20));
+  static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), G));
+  const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
+  BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
+  BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  BK_CUDA(cudaFuncSetAttribute(sb_larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * 2 * b * b)));
+  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)4 * b * n, ctx->stream));
+  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)4 * b * n, ctx->stream));
+  const size_t blk = (size_t)b * n;
+  cudaStream_t main_st = ctx->stream, side_st = ctx->side_stream;
+  // events: 0/1 ordering (columns ready, panel factored), 2.. timing pairs of the large GEMMs
+  cudaEvent_t e_col = pool_event(ctx, 0), e_fact = pool_event(ctx, 1);
+  size_t n_ev = 2;
+  double flops = 0.0;
+  auto mark = [&]() {
+    if (!stats) return;
+    cudaEventRecord(pool_event(ctx, n_ev++), ctx->stream);
+  };
+
+  // QR of the panel at columns c0 on the CURRENT ctx->stream: V -> Vd, Vd2; T -> Tk; VT = V T
+  auto factor_panel = [&](int c0, double* Vd, double* Vd2, double* Tk) -> int {
+    const int r0 = c0 + b, m = n - r0;
+    PanelArgs pa;
+    pa.A = A;
+    pa.lda = lda;
+    pa.n = n;
+    pa.c0 = c0;
+    pa.V = Vd;
+    pa.V2 = Vd2;
+    pa.ldv = n;
+    pa.taus = taus.p;
+    pa.part = part.p;
+    pa.prow = prow.p;
+    pa.barrier = ctx->barrier.p;
+    pa.prof = nullptr;
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(G, ceil_div(m, rows_target)));
+    pa.rows_per = (int)ceil_div(m, Gp);
+    BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
+    void* kargs[] = {&pa};
+    const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, ctx->stream));
+    BK_LAUNCHED(ctx);
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vd + r0, n, Vd + r0, n, 0.0, S.p, b));
+    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
+    BK_LAUNCHED(ctx);
+    BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vd + r0, n, Tk, b, 0.0, VT.p, m));
+    return BK_OK;
+  };
+
+  int k = 0;
+  bool on_side = false;  // the current panel was factored on the side stream
+  if (n - b >= 2) BK_TRY(factor_panel(0, PAbuf.p, PBbuf.p + blk, Tstore));
+  for (int c0 = 0; c0 < n; c0 += b, ++k) {
+    const int r0 = c0 + b, m = n - r0;
+    if (m < 2) break;
+    const int q = k & 1;
+    double* PA = PAbuf.p + (size_t)q * 2 * blk;  // [V | W] of this panel
+    double* PB = PBbuf.p + (size_t)q * 2 * blk;  // [W | V]
+    double* Tk = Tstore + (size_t)k * b * b;
+    double* A22 = A + r0 + (long long)r0 * lda;
+    if (on_side) BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+    mark();
+    BK_TRY(gemm(ctx, false, false, m, b, m, 1.0, A22, lda, VT.p, m, 0.0, PA + blk + r0, n));  // Z = A22 V T
+    mark();
+    flops += 2.0 * m * (double)m * b;
+    // W = Z - V (T' V'Z) / 2 in place, and the copy into [W | V]
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + blk + r0, n, 0.0, S2.p, b));
+    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));
+    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, PA + r0, n, S3.p, b, 1.0, PA + blk + r0, n));
+    BK_TRY(copy_matrix(ctx, PA + blk + r0, n, m, b, 1.0, PB + r0, n));
+    const int r1 = r0 + b, m2 = n - r1;
+    if (m2 < 2) {
+      // last panel: the whole trailing block (its lower triangle carries the final diagonal blocks of the band)
+      mark();
+      BK_TRY(gemm(ctx, false, true, m, m, 2 * b, -1.0, PA + r0, n, PB + r0, n, 1.0, A22, lda, 2));
+      mark();
+      flops += 1.0 * m * (double)m * 2 * b;
+      on_side = false;
+      continue;
+    }
+    // the next panel's columns (rows r0.., incl. its diagonal block) get the update first ...
+    BK_TRY(gemm(ctx, false, true, m, b, 2 * b, -1.0, PA + r0, n, PB + r0, n, 1.0, A22, lda));
+    BK_CUDA(cudaEventRecord(e_col, main_st));
+    // ... so that its factorisation can start on the side stream while the rest of the update runs here
+    {
+      BK_CUDA(cudaStreamWaitEvent(side_st, e_col, 0));
+      SideStreamScope sc(ctx);
+      double* PAn = PAbuf.p + (size_t)(q ^ 1) * 2 * blk;
+      double* PBn = PBbuf.p + (size_t)(q ^ 1) * 2 * blk;
+      BK_TRY(factor_panel(r0, PAn, PBn + blk, Tstore + (size_t)(k + 1) * b * b));
+      BK_CUDA(cudaEventRecord(e_fact, side_st));
+    }
+    on_side = true;
+    mark();
+    BK_TRY(gemm(ctx, false, true, m2, m2, 2 * b, -1.0, PA + r1, n, PB + r1, n, 1.0, A + r1 + (long long)r1 * lda, lda, 2));
+    mark();
+    flops += 1.0 * m2 * (double)m2 * 2 * b;
+  }
+  if (on_side) BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+  extract_band_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * ldab, 256), 16LL * ctx->sm_count), 256, 0,
+                        ctx->stream>>>(A, lda, n, b, AB, ldab);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    double sec = 0.0;
+    for (size_t i = 2; i + 1 < n_ev; i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->event_pool[i], ctx->event_pool[i + 1]);
+      sec += ms * 1e-3;
+    }
+    stats->gemm_launches = (double)((n_ev - 2) / 2);
+    stats->gemm_seconds = sec;
+    stats->gemm_flops = flops;
+  }
+  return BK_OK;
+}
+
 int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab, BandStats* stats) {
   const int b = SB;
   BK_REQUIRE(ldab >= 2 * b, "sy2sb: band storage needs 2b rows");
+  if (const char* la = getenv("BK_SY2SB_LOOKAHEAD"))
+    if (atoi(la) != 0) return sy2sb_lookahead(ctx, A, lda, n, Tstore, AB, ldab, stats);
   const int G = ctx->sm_count;
   DevBuf<double> taus, part, prow, S, T, VT, S2, S3;
   BK_TRY(taus.alloc(b));
@@ -399,6 +544,295 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     stats->gemm_launches = (double)(ev.size() / 2);
     stats->gemm_seconds = sec;
     stats->gemm_flops = flops;
+  }
+  return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Distributed dense -> band over the ranks of a peer communicator (SURVEY 8 f4 / e-S2).
+//
+// The trailing matrix is distributed by COLUMN BLOCKS of width b, block-cyclically: global block J lives on rank
+// J mod G as local block J / G (full columns, so the symmetric matrix is stored twice across the machine; every
+// rank then updates only its own columns and no reduction is needed).  Per panel J (owner o = J mod G):
+//
+//   o      : Householder QR of the panel (cooperative kernel above), T from V'V
+//   o -> * : the factored panel (R, V, rows c0..n) and T are STORED INTO EVERY OTHER RANK'S HBM over NVLink
+//            (peer_push2d) and a flag is raised                                             [b (m+b) doubles]
+//   all    : V T;   Z_g = A[:, own active columns]' (V T)   - the rows of Z = A22 V T that this rank owns;
+//            scattered into every rank's Z buffer by the same kind of peer stores           [all-gather, m b doubles]
+//   all    : W = Z - 1/2 V (T' (V'Z))  (replicated, tiny),   A[:, own columns] -= V W_g' + W V_g'
+//
+// Everything is ordered by system-scope flags inside kernels on the library stream: no host synchronisation, no
+// NCCL call.  Every rank also deposits every factored panel into its full-size matrix `Afact`, so that at the end
+// each rank holds exactly what the single-GPU sy2sb leaves behind (band + reflectors + T factors) and the
+// band -> tridiagonal stage and the back-transformations run unchanged.
+// Work per rank: 6 m^2 b / G flops per panel against 4 m^2 b on one GPU (the symmetry saving of the update is
+// traded for independence).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void dist_unpack_panel_kernel(const double* __restrict__ src, long long lds, int n, int c0, int wcols,
+                                         double* __restrict__ Afact, long long lda, double* __restrict__ V,
+                                         double* __restrict__ V2, long long ldv, bool write_v) {
+  // src: rows c0..n-1 (row index relative to c0), SB columns.  Afact[c0.., c0..c0+SB) = src; explicit V for rows >= r0
+  const int rows = n - c0;
+  const int m = rows - SB, nr = min(SB, m - 1);
+  const long long total = (long long)rows * wcols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % rows), l = (int)(idx / rows);
+    const double x = src[r + (long long)l * lds];
+    Afact[(long long)(c0 + r) + (long long)(c0 + l) * lda] = x;
+    if (write_v && r >= SB) {
+      const int pr = r - SB;  // panel row
+      double v = 0.0;
+      if (l < nr) v = (pr > l) ? x : (pr == l ? 1.0 : 0.0);
+      V[(long long)(c0 + r) + (long long)l * ldv] = v;
+      V2[(long long)(c0 + r) + (long long)l * ldv] = v;
+    }
+  }
+}
+
+// Zloc (nact x SB, local column order) -> rows of every rank's Z buffer (global row = global column index), flag
+__global__ void __launch_bounds__(256) dist_zpush_kernel(PeerDev pd, const double* __restrict__ Zloc, int nact, int lc0,
+                                                         size_t z_off, long long ldz, unsigned dst_mask, unsigned seq) {
+  const long long total = (long long)nact * SB;
+  for (int r = 0; r < pd.world; ++r) {
+    if (!(dst_mask & (1u << r))) continue;
+    double* Z = reinterpret_cast<double*>(pd.heap[r] + z_off);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+      const int i = (int)(idx % nact), j = (int)(idx / nact);
+      const int lc = lc0 + i;
+      const long long grow = ((long long)(lc / SB) * pd.world + pd.rank) * SB + (lc % SB);
+      Z[grow + (long long)j * ldz] = Zloc[i + (long long)j * nact];
+    }
+  }
+  peer_signal_last_cta(pd, peer_counter(pd, CH_ZGATHER), gridDim.x, dst_mask, CH_ZGATHER, seq);
+}
+
+// dst (nact x cols) = rows of src (ld lds) at the global indices of this rank's local columns lc0 .. lc0+nact-1
+__global__ void dist_gather_rows_kernel(const double* __restrict__ src, long long lds, int nact, int lc0, int cols,
+                                        int rank, int world, double* __restrict__ dst) {
+  const long long total = (long long)nact * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nact), j = (int)(idx / nact);
+    const int lc = lc0 + i;
+    const long long grow = ((long long)(lc / SB) * world + rank) * SB + (lc % SB);
+    dst[i + (long long)j * nact] = src[grow + (long long)j * lds];
+  }
+}
+
+// Xg (ncl x p) = rows of X at this rank's global columns
+__global__ void dist_gather_x_kernel(const double* __restrict__ X, long long ldx, int p, int ncl, int rank, int world,
+                                     double* __restrict__ Xg) {
+  const long long total = (long long)ncl * p;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % ncl), j = (int)(idx / ncl);
+    const long long grow = ((long long)(i / SB) * world + rank) * SB + (i % SB);
+    Xg[i + (long long)j * ncl] = X[grow + (long long)j * ldx];
+  }
+}
+
+// number of valid local columns of `rank` for an n x n matrix
+static int dist_local_cols(int n, int rank, int world) {
+  const int nb = (int)ceil_div(n, SB);
+  int cols = 0;
+  for (int J = rank; J < nb; J += world) cols += std::min(SB, n - J * SB);
+  return cols;
+}
+
+size_t sy2sb_dist_heap_bytes(int n) {
+  // two panel receive buffers (n x b + T), two Z buffers (n x b)
+  return sizeof(double) * (2 * ((size_t)n * SB + SB * SB + 256) + 2 * (size_t)n * SB) + 4096;
+}
+
+int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n, double* Afact,
+               double* Tstore, double* AB, int ldab, DevBuf<double>& aloc_cache, BandStats* stats) {
+  const int b = SB, G = peer->world, g = peer->rank;
+  BK_REQUIRE(ldab >= 2 * b, "sy2sb: band storage needs 2b rows");
+  cudaStream_t st = ctx->stream;
+  const int ncl = dist_local_cols(n, g, G);
+  const long long lda = n;
+  const unsigned all = (1u << G) - 1u, others = all & ~(1u << g);
+
+  // ---- symmetric buffers -------------------------------------------------------------------------------
+  size_t vrecv_off[2], z_off[2];
+  const size_t panel_elems = (size_t)n * b;
+  for (int q = 0; q < 2; ++q) BK_TRY(peer_alloc(peer, sizeof(double) * (panel_elems + b * b + 256), &vrecv_off[q]));
+  for (int q = 0; q < 2; ++q) BK_TRY(peer_alloc(peer, sizeof(double) * panel_elems, &z_off[q]));
+
+  // ---- local buffers -----------------------------------------------------------------------------------
+  DevBuf<double> Aloc, Xg, taus, part, prow, S, VT, S2, S3, PAbuf, PBbuf, Zloc, PBc;
+  BK_TRY(Aloc.borrow(aloc_cache, (size_t)n * std::max(1, ncl)));
+  BK_TRY(Xg.alloc((size_t)std::max(1, ncl) * p));
+  BK_TRY(taus.alloc(b));
+  BK_TRY(part.alloc((size_t)2 * ctx->sm_count * b));
+  BK_TRY(prow.alloc(2 * b));
+  BK_TRY(S.alloc(b * b));
+  BK_TRY(VT.alloc((size_t)n * b));
+  BK_TRY(S2.alloc(b * b));
+  BK_TRY(S3.alloc(b * b));
+  BK_TRY(PAbuf.alloc((size_t)2 * b * n));
+  BK_TRY(PBbuf.alloc((size_t)2 * b * n));
+  BK_TRY(Zloc.alloc((size_t)std::max(1, ncl) * b));
+  BK_TRY(PBc.alloc((size_t)std::max(1, ncl) * 2 * b));
+  BK_TRY(ctx->barrier.ensure(4));
+  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)2 * b * n, st));
+  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)2 * b * n, st));
+  double* const PA = PAbuf.p;  // [V | W]
+  double* const PB = PBbuf.p;  // [W | V]
+  const size_t blk = (size_t)b * n;
+
+  static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), ctx->sm_count));
+  const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
+  BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
+  BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  BK_CUDA(cudaFuncSetAttribute(sb_larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * 2 * b * b)));
+
+  // ---- own columns of K straight from X (no gather of the kernel matrix) ---------------------------------
+  if (ncl > 0) {
+    dist_gather_x_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)ncl * p, 256), 8LL * ctx->sm_count), 256, 0,
+                           st>>>(X, ldx, p, ncl, g, G, Xg.p);
+    BK_LAUNCHED(ctx);
+    BK_TRY(gauss_kernel_rect(ctx, X, ldx, n, Xg.p, ncl, ncl, p, sigma, Aloc.p, lda));
+  }
+  // everyone's receive buffers are free (previous fit finished everywhere) before the first push
+  BK_TRY(peer_barrier(peer, st));
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double flops = 0.0;
+  int launches = 0;
+  if (stats) {
+    BK_CUDA(cudaEventCreate(&ev0));
+    BK_CUDA(cudaEventCreate(&ev1));
+  }
+  const int nbk = (int)ceil_div(n, b);
+  int J = 0;
+  for (; J < nbk; ++J) {
+    const int c0 = J * b, r0 = c0 + b, m = n - r0;
+    if (m < 2) break;
+    const int owner = J % G, lb = J / G, q = J & 1;
+    double* Tk = Tstore + (size_t)J * b * b;
+    const unsigned seqT = peer_next_seq(peer, CH_PANEL), seqP = peer_next_seq(peer, CH_PANEL);
+    double* vrecv = peer_ptr(peer, vrecv_off[q]);
+    if (g == owner) {
+      // ---- factor the panel in place in the local columns
+      PanelArgs pa;
+      pa.A = Aloc.p + ((long long)lb * b - c0) * lda;  // so that A[(r0+r) + (c0+l) lda] is the local column
+      pa.lda = lda;
+      pa.n = n;
+      pa.c0 = c0;
+      pa.V = PA;
+      pa.V2 = PB + blk;
+      pa.ldv = n;
+      pa.taus = taus.p;
+      pa.part = part.p;
+      pa.prow = prow.p;
+      pa.barrier = ctx->barrier.p;
+      pa.prof = nullptr;
+      const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, ceil_div(m, rows_target)));
+      pa.rows_per = (int)ceil_div(m, Gp);
+      BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, st));
+      void* kargs[] = {&pa};
+      const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
+      BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, st));
+      BK_LAUNCHED(ctx);
+      BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + r0, n, 0.0, S.p, b));
+      sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, st>>>(S.p, taus.p, b, Tk);
+      BK_LAUNCHED(ctx);
+      // ---- T, then the factored panel (rows c0..n: diagonal block, R, V), into every other rank's HBM
+      const double* pan = Aloc.p + c0 + (long long)lb * b * lda;
+      if (others) {
+        BK_TRY(peer_push2d(peer, Tk, b, b, b, vrecv_off[q] + sizeof(double) * panel_elems, b, others, CH_PANEL, seqT, st));
+        BK_TRY(peer_push2d(peer, pan, lda, n - c0, b, vrecv_off[q] + sizeof(double) * c0, n, others, CH_PANEL, seqP, st));
+      }
+      // own deposit (V is already explicit in PA / PB from the QR kernel)
+      dist_unpack_panel_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)(n - c0) * b, 256), 4LL * ctx->sm_count),
+                                 256, 0, st>>>(pan, lda, n, c0, b, Afact, n, PA, PB + blk, n, false);
+      BK_LAUNCHED(ctx);
+    } else {
+      BK_TRY(peer_wait(peer, CH_PANEL, 1u << owner, seqP, st));
+      dist_unpack_panel_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)(n - c0) * b, 256), 4LL * ctx->sm_count),
+                                 256, 0, st>>>(vrecv + c0, n, n, c0, b, Afact, n, PA, PB + blk, n, true);
+      BK_LAUNCHED(ctx);
+      BK_CUDA(cudaMemcpyAsync(Tk, vrecv + panel_elems, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, st));
+    }
+    BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, PA + r0, n, Tk, b, 0.0, VT.p, m));  // V T
+    // ---- own rows of Z = A22 (V T): the local active columns, transposed
+    const int lb0 = (J >= g) ? (J - g) / G + 1 : 0;  // local blocks with global index <= J are done
+    const int lc0 = lb0 * b;
+    const int nact = std::max(0, ncl - lc0);
+    const unsigned seqZ = peer_next_seq(peer, CH_ZGATHER);
+    if (stats) BK_CUDA(cudaEventRecord(ev0, st));
+    if (nact > 0)
+      BK_TRY(gemm(ctx, true, false, nact, b, m, 1.0, Aloc.p + r0 + (long long)lc0 * lda, lda, VT.p, m, 0.0, Zloc.p, nact));
+    if (stats) {
+      BK_CUDA(cudaEventRecord(ev1, st));
+      flops += 2.0 * nact * (double)m * b;
+      ++launches;
+    }
+    {
+      const long long tot = (long long)std::max(1, nact) * b;
+      dist_zpush_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 512), 2LL * ctx->sm_count), 256, 0, st>>>(
+          peer->dev, Zloc.p, nact, lc0, z_off[q], n, all, seqZ);
+      BK_LAUNCHED(ctx);
+    }
+    BK_TRY(peer_wait(peer, CH_ZGATHER, all, seqZ, st));
+    // ---- W = Z - 1/2 V (T' (V'Z))  (replicated)
+    const double* Zfull = peer_ptr(peer, z_off[q]);
+    BK_TRY(copy_matrix(ctx, Zfull + r0, n, m, b, 1.0, PA + blk + r0, n));
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + blk + r0, n, 0.0, S2.p, b));
+    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));
+    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, PA + r0, n, S3.p, b, 1.0, PA + blk + r0, n));
+    BK_TRY(copy_matrix(ctx, PA + blk + r0, n, m, b, 1.0, PB + r0, n));
+    // ---- A[:, own active columns] -= [V W] [W_g V_g]'
+    if (nact > 0) {
+      const long long tot = (long long)nact * 2 * b;
+      dist_gather_rows_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 256), 4LL * ctx->sm_count), 256, 0, st>>>(
+          PB, n, nact, lc0, 2 * b, g, G, PBc.p);
+      BK_LAUNCHED(ctx);
+      BK_TRY(gemm(ctx, false, true, m, nact, 2 * b, -1.0, PA + r0, n, PBc.p, nact, 1.0, Aloc.p + r0 + (long long)lc0 * lda,
+                  lda));
+      flops += 2.0 * m * (double)nact * 2 * b;
+    }
+  }
+  // ---- the remaining (unfactored) diagonal blocks reach everyone the same way
+  for (; J < nbk; ++J) {
+    const int c0 = J * b, owner = J % G, lb = J / G, q = J & 1;
+    const int w = std::min(b, n - c0);
+    peer_next_seq(peer, CH_PANEL);
+    const unsigned seqP = peer_next_seq(peer, CH_PANEL);
+    double* vrecv = peer_ptr(peer, vrecv_off[q]);
+    const long long tot = (long long)(n - c0) * w;
+    const unsigned nblk = (unsigned)std::min<long long>(ceil_div(tot, 256), 4LL * ctx->sm_count);
+    if (g == owner) {
+      const double* pan = Aloc.p + c0 + (long long)lb * b * lda;
+      if (others) BK_TRY(peer_push2d(peer, pan, lda, n - c0, w, vrecv_off[q] + sizeof(double) * c0, n, others, CH_PANEL, seqP, st));
+      dist_unpack_panel_kernel<<<nblk, 256, 0, st>>>(pan, lda, n, c0, w, Afact, n, PA, PB + blk, n, false);
+      BK_LAUNCHED(ctx);
+    } else {
+      BK_TRY(peer_wait(peer, CH_PANEL, 1u << owner, seqP, st));
+      dist_unpack_panel_kernel<<<nblk, 256, 0, st>>>(vrecv + c0, n, n, c0, w, Afact, n, PA, PB + blk, n, false);
+      BK_LAUNCHED(ctx);
+    }
+  }
+  extract_band_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * ldab, 256), 16LL * ctx->sm_count), 256, 0,
+                        st>>>(Afact, n, n, b, AB, ldab);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(cudaGetLastError());
+  // nobody re-uses (resets) the symmetric buffers before every rank is through
+  BK_TRY(peer_barrier(peer, st));
+  BK_TRY(peer_check(peer, st));
+  if (stats) {
+    // the Z-product GEMM of the LAST panel only is bracketed (events are re-recorded); the totals are flops
+    stats->gemm_launches = launches;
+    stats->gemm_flops = flops;
+    stats->gemm_seconds = 0.0;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
   }
   return BK_OK;
 }
