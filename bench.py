@@ -247,6 +247,104 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+OTHER_CONFIGS = {
+    2: dict(N=10000, P=10, seed=1002, kw=dict(eigtrunc=0.0), fixture="c2_N10000_P10",
+            name="N=10k P=10 full eigendecomposition, all marginal effects (BASELINE.json configs[1])"),
+    4: dict(N=60000, P=20, seed=1004, kw=dict(Neig=500, which_derivatives=[1, 3, 5]), fixture=None,
+            name="N=60k P=20 Neig=500 truncated eig, which.derivatives=c(1,3,5) (BASELINE.json configs[3])"),
+    5: dict(N=20000, P=10, seed=1005, kw=dict(), fixture="c5_cv_N20000_P10",
+            name="crossvalidate.bigKRLS Kfolds=5 on N=20k P=10, folds sharded across the GPUs (BASELINE.json configs[4])"),
+}
+
+
+def run_other_config(args):
+    """The other BASELINE.json configurations as bench lines (not the headline metric): the public API end to end
+    with host buffers, seconds per call, max over ranks."""
+    import torch
+    from bigkrls_b200 import _lib, bigKRLS, crossvalidate_bigKRLS
+    cfg = OTHER_CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        from bigkrls_b200.dist import TorchComm
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = TorchComm(device=f"cuda:{local}", ctx=_lib.default_context(local))
+    ctx = _lib.default_context(local)
+    N, P = cfg["N"], cfg["P"]
+    X, y = synthetic(N, P, cfg["seed"])
+    # the three N x N outputs travel to the host only when a rank's share is moderate (config 4 on one GPU would be
+    # 3 x 28.8 GB of pinned host memory)
+    squares = (8.0 * N * N / world) <= 8e9
+    infos, parity = [], None
+
+    def step():
+        if args.config == 5:
+            folds = np.random.default_rng(cfg["seed"]).permutation(N) % 5 + 1
+            return crossvalidate_bigKRLS(y, X, folds=folds, comm=comm, ctx=ctx)
+        fit = bigKRLS(y, X, comm=comm, ctx=ctx, pinned=True, return_squares=squares, **cfg["kw"])
+        info = dict(fit["_info"])
+        info["lambda"], info["lastkeeper"] = fit["lambda"], fit["lastkeeper"]
+        fit.release_device()
+        fit.release_pinned()
+        return info
+
+    def sync():
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sync()
+    launches0 = _lib.load().bk_launch_count(ctx.handle)
+    sampler.start()
+    t0 = time.perf_counter()
+    outs = [step() for _ in range(args.steps)]
+    sync()
+    sec = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    launches = _lib.load().bk_launch_count(ctx.handle) - launches0
+    if comm is not None:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        sec = float(t.item())
+    if rank == 0:
+        last = outs[-1]
+        line = {"metric": "bigKRLS wall-s, " + cfg["name"], "value": sec, "unit": "s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": cfg["name"], "seed": cfg["seed"], "N": N, "P": P,
+                           "l2": "inputs larger than L2", "outputs_to_host": "K, vcov.est.c, vcov.est.fitted + vectors"
+                           if squares else "vectors only (N x N fields stay on the device)"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
+                        "d2h_bytes_per_step": int((3 * 8 * N * N / world if squares and args.config != 5 else 0) + 8 * N * (P + 3))},
+                "note": "value == e2e here: these lines time the public API with host buffers only"}
+        if args.config == 5:
+            line["cv"] = {k: [float(v) for v in last[k]] for k in ("R2_oos", "MSE_oos") if k in last}
+            try:
+                z = np.load(os.path.join(ROOT, "tests", "golden", cfg["fixture"] + ".npz"))
+                line["parity_vs_oracle_fixture"] = {k: float(np.max(np.abs(np.asarray(last[k]) - z[k])) / np.max(np.abs(z[k])))
+                                                    for k in ("R2_is", "R2_oos", "MSE_is", "MSE_oos", "R2AME_oos", "MSE_AME_oos")}
+            except Exception:  # noqa: BLE001
+                pass
+        else:
+            line["stage_seconds"] = {k: float(last[k]) for k in ("t_kernel", "t_eigen", "t_lambda", "t_coef", "t_vcov",
+                                                                  "t_deriv", "t_total")}
+            line["fit"] = {"lambda": last["lambda"], "lastkeeper": int(last["lastkeeper"]),
+                           "krylov_matvecs": int(last.get("krylov_matvecs", 0)),
+                           "krylov_restarts": int(last.get("krylov_restarts", 0))}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,9 +355,13 @@ def main():
     ap.add_argument("--p", type=int, default=P_FULL)
     ap.add_argument("--sample-n", type=int, default=3000, help="rows of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[] index + 1 of the workload (3 = the headline metric, the default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != 3:
+        return run_other_config(args)
 
     import torch
     import ctypes as C
@@ -347,6 +449,8 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         sec, e2e_sec = t.tolist()
     if rank != 0:
+        comm.close()
+        torch.distributed.destroy_process_group()
         return
     info = infos[-1]
     if info.get("twostage", 0) > 0:
@@ -452,6 +556,7 @@ def main():
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
     if comm is not None:
+        comm.close()
         torch.distributed.destroy_process_group()
 
 

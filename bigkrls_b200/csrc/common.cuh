@@ -6,8 +6,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <stdarg.h>
+#include <time.h>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/bigkrls_b200.h"
 
@@ -52,12 +54,27 @@ inline bool pool_enabled() {
   return on;
 }
 
+// Large device blocks (>= 8 MB) bypass the driver's stream-ordered pool: they are cudaMalloc'ed once and parked in
+// a per-(device, stream) exact-size free list when released, so that the multi-GB matrices of a fit (K, the
+// eigenvector block, the two vcov matrices) are the SAME blocks in every fit.  The driver pool was measured to miss
+// on them (60-700 ms per 3.2 GB block, every fit) as soon as smaller allocations interleave with them; its reuse
+// is a heuristic, this is not.  Reuse is safe in stream order because a block only ever returns to the stream it
+// was used on.  bk_trim / bk_destroy give the parked blocks back.
+void* big_cache_get(size_t bytes, cudaStream_t st, int dev);
+void big_cache_put(void* p, size_t bytes, cudaStream_t st, int dev);
+void big_cache_trim(int dev);
+static constexpr size_t kBigBlockBytes = (size_t)8 << 20;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaStream_t pool_stream = nullptr;  // stream the block was allocated on (stream-ordered pool)
   bool pooled = false;
+  bool cached = false;  // block belongs to the big-block free list (see big_cache_get)
+  int dev = 0;
+  bool plain = false;  // long-lived cache: plain cudaMalloc, never from the stream-ordered pool (a persistent block
+                       // in the middle of the pool fragments it and later multi-GB allocations fall off the fast path)
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -69,7 +86,9 @@ struct DevBuf {
       borrowed = false;
       return;
     }
-    if (p) {
+    if (p && cached) {
+      big_cache_put(p, n * sizeof(T), pool_stream, dev);
+    } else if (p) {
       // stream-ordered free: the block returns to the pool once the work queued so far has used it
       if (!pooled || cudaFreeAsync(p, pool_stream) != cudaSuccess) {
         cudaGetLastError();
@@ -79,17 +98,33 @@ struct DevBuf {
     p = nullptr;
     n = 0;
     pooled = false;
+    cached = false;
   }
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
     cudaError_t e;
-    if (pool_enabled()) {
+    static const bool verbose = getenv("BK_ALLOC_VERBOSE") != nullptr;
+    struct timespec t0_, t1_;
+    if (verbose) clock_gettime(CLOCK_MONOTONIC, &t0_);
+    if (pool_enabled() && !plain && count * sizeof(T) >= kBigBlockBytes) {
+      pool_stream = alloc_stream();
+      cudaGetDevice(&dev);
+      p = (T*)big_cache_get(count * sizeof(T), pool_stream, dev);
+      cached = (p != nullptr);
+      e = cached ? cudaSuccess : cudaGetLastError();
+      if (!cached && e == cudaSuccess) e = cudaErrorMemoryAllocation;
+    } else if (pool_enabled() && !plain) {
       pool_stream = alloc_stream();
       e = cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream);
       pooled = (e == cudaSuccess);
     } else {
       e = cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    if (verbose) {
+      clock_gettime(CLOCK_MONOTONIC, &t1_);
+      const double ms = (t1_.tv_sec - t0_.tv_sec) * 1e3 + (t1_.tv_nsec - t0_.tv_nsec) * 1e-6;
+      if (ms > 1.0) fprintf(stderr, "[alloc] %.1f MB took %.2f ms (%s)\n", count * sizeof(T) * 1e-6, ms, (pooled ? "pool" : "cudaMalloc"));
     }
     if (e != cudaSuccess) {
       p = nullptr;
@@ -119,6 +154,17 @@ struct DevBuf {
     return BK_OK;
   }
   bool borrowed = false;
+  // exchange the blocks (and their provenance) of two buffers
+  void swap_block(DevBuf& o) {
+    std::swap(p, o.p);
+    std::swap(n, o.n);
+    std::swap(pool_stream, o.pool_stream);
+    std::swap(pooled, o.pooled);
+    std::swap(cached, o.cached);
+    std::swap(dev, o.dev);
+    std::swap(plain, o.plain);
+    std::swap(borrowed, o.borrowed);
+  }
 };
 
 struct Timer {
@@ -162,6 +208,7 @@ struct bk_ctx {
   cudaStream_t side_stream = nullptr;  // high-priority stream for look-ahead work (panel factorisation under an update)
   bk::DevBuf<double> gemm_ws;          // split-K partials
   bk::DevBuf<double> gemm_ws_side;     // the same for GEMMs issued on the side stream
+  bk::DevBuf<double> panel_cache[2];   // [V W] / [W V] panel buffers of the dense->band stage (grow-only)
   std::vector<cudaEvent_t> event_pool; // timing / ordering events reused across fits (created on first use)
   bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
   bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
@@ -278,17 +325,11 @@ struct SideStreamScope {
   cudaStream_t saved;
   SideStreamScope(bk_ctx* ctx) : c(ctx), saved(ctx->stream) {
     c->stream = c->side_stream;
-    std::swap(c->gemm_ws.p, c->gemm_ws_side.p);
-    std::swap(c->gemm_ws.n, c->gemm_ws_side.n);
-    std::swap(c->gemm_ws.pooled, c->gemm_ws_side.pooled);
-    std::swap(c->gemm_ws.pool_stream, c->gemm_ws_side.pool_stream);
+    c->gemm_ws.swap_block(c->gemm_ws_side);
   }
   ~SideStreamScope() {
     c->stream = saved;
-    std::swap(c->gemm_ws.p, c->gemm_ws_side.p);
-    std::swap(c->gemm_ws.n, c->gemm_ws_side.n);
-    std::swap(c->gemm_ws.pooled, c->gemm_ws_side.pooled);
-    std::swap(c->gemm_ws.pool_stream, c->gemm_ws_side.pool_stream);
+    c->gemm_ws.swap_block(c->gemm_ws_side);
   }
 };
 // i-th event of the context's pool (timing enabled), created on first use

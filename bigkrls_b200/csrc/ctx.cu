@@ -4,7 +4,65 @@
 #include "dgemm.cuh"
 #include "kernels.cuh"
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace bk {
+namespace {
+struct BigCache {
+  std::mutex mu;
+  std::map<std::tuple<int, cudaStream_t, size_t>, std::vector<void*>> free_blocks;
+};
+BigCache& big_cache() {
+  static BigCache c;
+  return c;
+}
+}  // namespace
+
+void* big_cache_get(size_t bytes, cudaStream_t st, int dev) {
+  {
+    BigCache& c = big_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.free_blocks.find(std::make_tuple(dev, st, bytes));
+    if (it != c.free_blocks.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    // out of memory with blocks parked in the free list: give them back and retry once
+    cudaGetLastError();
+    big_cache_trim(dev);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  }
+  return p;
+}
+void big_cache_put(void* p, size_t bytes, cudaStream_t st, int dev) {
+  BigCache& c = big_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  c.free_blocks[std::make_tuple(dev, st, bytes)].push_back(p);
+}
+void big_cache_trim(int dev) {
+  BigCache& c = big_cache();
+  std::vector<void*> victims;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto it = c.free_blocks.begin(); it != c.free_blocks.end();) {
+      if (std::get<0>(it->first) == dev) {
+        victims.insert(victims.end(), it->second.begin(), it->second.end());
+        it = c.free_blocks.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  if (!victims.empty()) cudaDeviceSynchronize();
+  for (void* p : victims) cudaFree(p);
+}
+
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -59,6 +117,10 @@ int bk_init(int device, bk_ctx** out) {
   }
   bk::alloc_stream() = c->stream;
   c->copier = bk::copier_create(device, c->copy_stream);
+  c->gemm_ws_side.plain = true;
+  c->panel_cache[0].plain = c->panel_cache[1].plain = true;
+  c->counters.plain = true;
+  BK_TRY(c->gemm_ws_side.alloc((size_t)4 << 20));
   BK_TRY(c->counters.alloc(64));
   BK_CUDA(cudaMemsetAsync(c->counters.p, 0, 64 * sizeof(unsigned), c->stream));
   *out = c;
@@ -74,6 +136,8 @@ void bk_destroy(bk_ctx* ctx) {
   ctx->copier = nullptr;
   ctx->gemm_ws.release();
   ctx->gemm_ws_side.release();
+  ctx->panel_cache[0].release();
+  ctx->panel_cache[1].release();
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   ctx->event_pool.clear();
   ctx->barrier.release();
@@ -81,6 +145,7 @@ void bk_destroy(bk_ctx* ctx) {
   ctx->counters.release();
   for (auto& w : ctx->ws) w.release();
   cudaStreamSynchronize(ctx->stream);
+  bk::big_cache_trim(ctx->device);
   if (bk::pool_enabled()) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -98,8 +163,10 @@ int bk_trim(bk_ctx* ctx) {
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   for (auto& w : ctx->ws) w.release();
   ctx->gemm_ws.release();
-  ctx->gemm_ws_side.release();
+  ctx->panel_cache[0].release();
+  ctx->panel_cache[1].release();
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  bk::big_cache_trim(ctx->device);
   if (bk::pool_enabled()) {
     cudaMemPool_t pool;
     BK_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));

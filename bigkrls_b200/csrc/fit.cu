@@ -98,6 +98,30 @@ int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
   return s < thr ? -1 : (s > thr ? 1 : 0);
 }
 
+// Approximate real root of sum(ev/(ev+x)) = thr on x > 0 (the function is convex and decreasing there) by a few
+// Newton steps in plain double - only a STARTING GUESS for the exact integer searches below, which verify it with
+// the reference's own comparisons.
+double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
+  double x = x0;
+  for (int it = 0; it < 12; ++it) {
+    double f = 0.0, g = 0.0;
+    for (double e : ev) {
+      const double d = e + x, r = e / d;
+      f += r;
+      g -= r / d;
+    }
+    if (!(g < 0.0) || !std::isfinite(f)) break;
+    const double xn = x - (f - thr) / g;
+    const double nx = (xn > 0.0) ? xn : 0.5 * x;  // Newton from the left of a convex decreasing function stays left
+    if (std::fabs(nx - x) <= 1e-3 * std::max(1.0, std::fabs(x)) * 1e-3) {
+      x = nx;
+      break;
+    }
+    x = nx;
+  }
+  return x;
+}
+
 int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
   if (!(*U > 0.0)) {
     // Reference (R/bigKRLS_Rcpp_functions.R:16-20): U = n; while (sum(ev/(ev+U)) < 1) U = U - 1 - hundreds to
@@ -108,6 +132,20 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
     long long lo = 0, hi = -1;
     if (ok(0)) {
       hi = 0;
+    } else if ([&]() {
+                 // Newton guess for the crossing, then the scan's own stopping rule on the two neighbouring integers
+                 const double xr = ratio_root_guess(ev, 1.0, 0.5 * (double)n);
+                 if (!(xr > 1.0) || !(xr < (double)n)) return false;
+                 for (long long m = (long long)n - (long long)std::floor(xr) - 1, t = 0; t < 3; ++m, ++t) {
+                   if (m < 1 || m > (long long)n - 1) continue;
+                   if (ok(m) && !ok(m - 1)) {
+                     hi = m;
+                     return true;
+                   }
+                 }
+                 return false;
+               }()) {
+      // hi = first passing offset, verified: hi - 1 fails
     } else {
       long long step = 1;
       while (hi < 0) {  // gallop: lo is always a failing offset
@@ -152,7 +190,19 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
     };
     auto stop = [&](size_t i) { return ratio_cmp(ev, cand(i), (double)q) <= 0; };  // loop test false
     size_t lo = 0, hi = 0;
-    if (!stop(0)) {
+    bool found = stop(0);
+    if (!found) {
+      const double xr = ratio_root_guess(ev, (double)q, 1.0);
+      if (xr > 0.0 && xr < 4e6) {
+        const long long i0 = (long long)std::ceil((xr - ls[0]) / 0.05);
+        for (long long i = std::max(1LL, i0 - 1), t = 0; t < 3 && !found; ++i, ++t)
+          if (stop((size_t)i) && !stop((size_t)i - 1)) {
+            hi = (size_t)i;
+            found = true;
+          }
+      }
+    }
+    if (!found) {
       size_t step = 1;
       for (;;) {
         const size_t m = lo + step;
@@ -486,10 +536,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
                               ctx->stream));
       BK_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
-      std::swap(f->Q.p, Zfull.p);
-      std::swap(f->Q.n, Zfull.n);
-      std::swap(f->Q.pooled, Zfull.pooled);
-      std::swap(f->Q.pool_stream, Zfull.pool_stream);
+      f->Q.swap_block(Zfull);
     }
   }
   f->k = k;

@@ -256,10 +256,9 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
   BK_TRY(VT.alloc((size_t)n * b));
   BK_TRY(S2.alloc(b * b));
   BK_TRY(S3.alloc(b * b));
-  BK_TRY(PAbuf.alloc((size_t)4 * b * n));
-  BK_TRY(PBbuf.alloc((size_t)4 * b * n));
+  BK_TRY(PAbuf.borrow(ctx->panel_cache[0], (size_t)4 * b * n));
+  BK_TRY(PBbuf.borrow(ctx->panel_cache[1], (size_t)4 * b * n));
   BK_TRY(ctx->barrier.ensure(4));
-  BK_TRY(ctx->gemm_ws_side.ensure((size_t)4 << 20));
   static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
   const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), G));
   const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
@@ -406,14 +405,12 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
                                (int)(sizeof(double) * 2 * b * b)));
   static const bool full_update = getenv("BK_SY2SB_FULL") != nullptr;
   // CUDA events around the two large GEMMs of every panel (roofline of the dominant kernel, bench.py)
-  std::vector<cudaEvent_t> ev;
+  // (events come from the context's pool: created once, reused by every fit)
+  size_t n_ev = 2;
   double flops = 0.0;
   auto mark = [&]() {
     if (!stats) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, ctx->stream);
-    ev.push_back(e);
+    cudaEventRecord(pool_event(ctx, n_ev++), ctx->stream);
   };
   DevBuf<long long> prof;
   if (getenv("BK_QR_PROF")) {
@@ -426,15 +423,28 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   //   Z2 -= [V1 W1] ([W1 V1]' V2 T2),
   // and one rank-4b update A22 -= [V1 W1 V2 W2][W1 V1 W2 V2]' follows.  PA = [V1|W1|V2|W2], PB = [W1|V1|W2|V2].
   static const bool pair_panels = getenv("BK_SY2SB_NOPAIR") == nullptr;
+  // Look-ahead: the FIRST panel of the next pair is factored on the high-priority side stream under the rank-4b
+  // update of this pair (its columns get the update first).  [V W] / [W V] are therefore double-buffered by pair
+  // parity: QR writes the next V1 while the update still reads this pair's panels.
+  static const bool pair_lookahead = getenv("BK_SY2SB_NOLA") == nullptr;
   DevBuf<double> PAbuf, PBbuf, Gs;
-  BK_TRY(PAbuf.alloc((size_t)4 * b * n));
-  BK_TRY(PBbuf.alloc((size_t)4 * b * n));
+  BK_TRY(PAbuf.borrow(ctx->panel_cache[0], (size_t)8 * b * n));
+  BK_TRY(PBbuf.borrow(ctx->panel_cache[1], (size_t)8 * b * n));
   BK_TRY(Gs.alloc((size_t)2 * b * b));
-  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)4 * b * n, ctx->stream));
-  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)4 * b * n, ctx->stream));
-  double* const PA = PAbuf.p;
-  double* const PB = PBbuf.p;
+  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)8 * b * n, ctx->stream));
+  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)8 * b * n, ctx->stream));
   const size_t blk = (size_t)b * n;
+  cudaStream_t main_st = ctx->stream, side_st = ctx->side_stream;
+  cudaEvent_t e_col = nullptr, e_fact = nullptr;
+  BK_CUDA(cudaEventCreateWithFlags(&e_col, cudaEventDisableTiming));
+  BK_CUDA(cudaEventCreateWithFlags(&e_fact, cudaEventDisableTiming));
+  struct EvGuard {
+    cudaEvent_t a, b;
+    ~EvGuard() {
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  } evguard{e_col, e_fact};
 
   // Householder QR of the panel at columns c0 (rows r0 = c0 + b ..): V into Vd and Vd2, T into Tk, VT = V T
   auto factor_panel = [&](int c0, double* Vd, double* Vd2, double* Tk) -> int {
@@ -475,14 +485,21 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     return BK_OK;
   };
 
-  int k = 0;
-  for (int c0 = 0; c0 < n;) {
+  int k = 0, pair = 0;
+  bool ahead = false;  // the first panel of this pair was factored on the side stream during the previous update
+  for (int c0 = 0; c0 < n; ++pair) {
     const int r0 = c0 + b, m = n - r0;
     if (m < 2) break;
+    double* PA = PAbuf.p + (size_t)(pair & 1) * 4 * blk;
+    double* PB = PBbuf.p + (size_t)(pair & 1) * 4 * blk;
     double* A22 = A + r0 + (long long)r0 * lda;
     double* T1 = Tstore + (size_t)k * b * b;
     // ---- first panel of the pair: V1 -> PA[0], PB[1]; W1 -> PA[1], PB[0]
-    BK_TRY(factor_panel(c0, PA, PB + blk, T1));
+    if (ahead)
+      BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+    else
+      BK_TRY(factor_panel(c0, PA, PB + blk, T1));
+    ahead = false;
     mark();
     BK_TRY(gemm(ctx, false, false, m, b, m, 1.0, A22, lda, VT.p, m, 0.0, PA + blk + r0, n));  // Z1 = A22 V1 T1
     mark();
@@ -512,14 +529,36 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     BK_TRY(gemm(ctx, true, false, 2 * b, b, m2, 1.0, PB + r1, n, VT.p, m2, 0.0, Gs.p, 2 * b));          // [W1 V1]' V2 T2
     BK_TRY(gemm(ctx, false, false, m2, b, 2 * b, -1.0, PA + r1, n, Gs.p, 2 * b, 1.0, PA + 3 * blk + r1, n));
     BK_TRY(finish_w(r1, PA + 2 * blk, PA + 3 * blk, PB + 2 * blk, T2));
-    // ---- one rank-4b update for both panels
-    mark();
-    BK_TRY(gemm(ctx, false, true, m2, m2, 4 * b, -1.0, PA + r1, n, PB + r1, n, 1.0, A22b, lda, 2));
-    mark();
-    flops += 1.0 * m2 * (double)m2 * 4 * b;
+    const int r2 = r1 + b, m3 = n - r2;
+    if (pair_lookahead && m3 >= 2) {
+      // ---- the next pair's first panel: its columns (rows r1.., incl. its diagonal block) get the rank-4b update
+      // first, then its factorisation runs on the side stream under the update of the trailing (m2-b) block
+      BK_TRY(gemm(ctx, false, true, m2, b, 4 * b, -1.0, PA + r1, n, PB + r1, n, 1.0, A22b, lda));
+      BK_CUDA(cudaEventRecord(e_col, main_st));
+      {
+        BK_CUDA(cudaStreamWaitEvent(side_st, e_col, 0));
+        SideStreamScope sc(ctx);
+        double* PAn = PAbuf.p + (size_t)((pair + 1) & 1) * 4 * blk;
+        double* PBn = PBbuf.p + (size_t)((pair + 1) & 1) * 4 * blk;
+        BK_TRY(factor_panel(r1, PAn, PBn + blk, Tstore + (size_t)(k + 2) * b * b));
+        BK_CUDA(cudaEventRecord(e_fact, side_st));
+      }
+      ahead = true;
+      mark();
+      BK_TRY(gemm(ctx, false, true, m3, m3, 4 * b, -1.0, PA + r2, n, PB + r2, n, 1.0, A + r2 + (long long)r2 * lda, lda, 2));
+      mark();
+      flops += 1.0 * m3 * (double)m3 * 4 * b;
+    } else {
+      // ---- one rank-4b update for both panels
+      mark();
+      BK_TRY(gemm(ctx, false, true, m2, m2, 4 * b, -1.0, PA + r1, n, PB + r1, n, 1.0, A22b, lda, 2));
+      mark();
+      flops += 1.0 * m2 * (double)m2 * 4 * b;
+    }
     c0 += 2 * b;
     k += 2;
   }
+  if (ahead) BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
   extract_band_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * ldab, 256), 16LL * ctx->sm_count), 256, 0,
                         ctx->stream>>>(A, lda, n, b, AB, ldab);
   BK_LAUNCHED(ctx);
@@ -535,13 +574,12 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   }
   if (stats) {
     double sec = 0.0;
-    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    for (size_t i = 2; i + 1 < n_ev; i += 2) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&ms, ctx->event_pool[i], ctx->event_pool[i + 1]);
       sec += ms * 1e-3;
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    stats->gemm_launches = (double)(ev.size() / 2);
+    stats->gemm_launches = (double)((n_ev - 2) / 2);
     stats->gemm_seconds = sec;
     stats->gemm_flops = flops;
   }
@@ -673,15 +711,13 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   BK_TRY(VT.alloc((size_t)n * b));
   BK_TRY(S2.alloc(b * b));
   BK_TRY(S3.alloc(b * b));
-  BK_TRY(PAbuf.alloc((size_t)2 * b * n));
-  BK_TRY(PBbuf.alloc((size_t)2 * b * n));
+  BK_TRY(PAbuf.borrow(ctx->panel_cache[0], (size_t)4 * b * n));  // [V | W] x 2 panel parities
+  BK_TRY(PBbuf.borrow(ctx->panel_cache[1], (size_t)4 * b * n));  // [W | V] x 2
   BK_TRY(Zloc.alloc((size_t)std::max(1, ncl) * b));
   BK_TRY(PBc.alloc((size_t)std::max(1, ncl) * 2 * b));
   BK_TRY(ctx->barrier.ensure(4));
-  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)2 * b * n, st));
-  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)2 * b * n, st));
-  double* const PA = PAbuf.p;  // [V | W]
-  double* const PB = PBbuf.p;  // [W | V]
+  BK_CUDA(cudaMemsetAsync(PAbuf.p, 0, sizeof(double) * (size_t)4 * b * n, st));
+  BK_CUDA(cudaMemsetAsync(PBbuf.p, 0, sizeof(double) * (size_t)4 * b * n, st));
   const size_t blk = (size_t)b * n;
 
   static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
@@ -702,59 +738,79 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   // everyone's receive buffers are free (previous fit finished everywhere) before the first push
   BK_TRY(peer_barrier(peer, st));
 
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double flops = 0.0;
   int launches = 0;
-  if (stats) {
-    BK_CUDA(cudaEventCreate(&ev0));
-    BK_CUDA(cudaEventCreate(&ev1));
-  }
   const int nbk = (int)ceil_div(n, b);
+  // Sequence numbers of the panel channel are a fixed function of the panel index (two per panel: T, panel), so that
+  // the owner of panel J+1 can push it from the side stream while panel J's update is still running everywhere.
+  const unsigned seq_base = peer->seq[CH_PANEL];
+  peer->seq[CH_PANEL] = seq_base + 2u * (unsigned)nbk;
+  auto seqT_of = [&](int J) { return seq_base + 2u * (unsigned)J + 1u; };
+  auto seqP_of = [&](int J) { return seq_base + 2u * (unsigned)J + 2u; };
+  static const bool lookahead = getenv("BK_DIST_NO_LOOKAHEAD") == nullptr;
+  cudaStream_t main_st = ctx->stream, side_st = ctx->side_stream;
+  cudaEvent_t e_col = pool_event(ctx, 0), e_fact = pool_event(ctx, 1);
+
+  // Owner side of panel J on the CURRENT ctx->stream: QR in the local columns, T, pushes, own deposit.
+  // PAq / PBq: the [V W] / [W V] buffers of this panel's parity.
+  auto owner_factor = [&](int J, double* PAq, double* PBq) -> int {
+    const int c0 = J * b, r0 = c0 + b, m = n - r0, lb = J / G, q = J & 1;
+    cudaStream_t cs = ctx->stream;
+    double* Tk = Tstore + (size_t)J * b * b;
+    PanelArgs pa;
+    pa.A = Aloc.p + ((long long)lb * b - c0) * lda;  // so that A[(r0+r) + (c0+l) lda] is the local column
+    pa.lda = lda;
+    pa.n = n;
+    pa.c0 = c0;
+    pa.V = PAq;
+    pa.V2 = PBq + blk;
+    pa.ldv = n;
+    pa.taus = taus.p;
+    pa.part = part.p;
+    pa.prow = prow.p;
+    pa.barrier = ctx->barrier.p;
+    pa.prof = nullptr;
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, ceil_div(m, rows_target)));
+    pa.rows_per = (int)ceil_div(m, Gp);
+    BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, cs));
+    void* kargs[] = {&pa};
+    const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
+    BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, cs));
+    BK_LAUNCHED(ctx);
+    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PAq + r0, n, PAq + r0, n, 0.0, S.p, b));
+    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, cs>>>(S.p, taus.p, b, Tk);
+    BK_LAUNCHED(ctx);
+    // T, then the factored panel (rows c0..n: diagonal block, R, V), into every other rank's HBM
+    const double* pan = Aloc.p + c0 + (long long)lb * b * lda;
+    if (others) {
+      BK_TRY(peer_push2d(peer, Tk, b, b, b, vrecv_off[q] + sizeof(double) * panel_elems, b, others, CH_PANEL, seqT_of(J), cs));
+      BK_TRY(peer_push2d(peer, pan, lda, n - c0, b, vrecv_off[q] + sizeof(double) * c0, n, others, CH_PANEL, seqP_of(J), cs));
+    }
+    // own deposit (V is already explicit in PA / PB from the QR kernel)
+    dist_unpack_panel_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)(n - c0) * b, 256), 4LL * ctx->sm_count),
+                               256, 0, cs>>>(pan, lda, n, c0, b, Afact, n, PAq, PBq + blk, n, false);
+    BK_LAUNCHED(ctx);
+    return BK_OK;
+  };
+
   int J = 0;
+  bool factored_ahead = false;  // this rank owns the current panel and factored it on the side stream already
   for (; J < nbk; ++J) {
     const int c0 = J * b, r0 = c0 + b, m = n - r0;
     if (m < 2) break;
-    const int owner = J % G, lb = J / G, q = J & 1;
+    const int owner = J % G, q = J & 1;
+    double* PA = PAbuf.p + (size_t)q * 2 * blk;  // [V | W]
+    double* PB = PBbuf.p + (size_t)q * 2 * blk;  // [W | V]
     double* Tk = Tstore + (size_t)J * b * b;
-    const unsigned seqT = peer_next_seq(peer, CH_PANEL), seqP = peer_next_seq(peer, CH_PANEL);
     double* vrecv = peer_ptr(peer, vrecv_off[q]);
     if (g == owner) {
-      // ---- factor the panel in place in the local columns
-      PanelArgs pa;
-      pa.A = Aloc.p + ((long long)lb * b - c0) * lda;  // so that A[(r0+r) + (c0+l) lda] is the local column
-      pa.lda = lda;
-      pa.n = n;
-      pa.c0 = c0;
-      pa.V = PA;
-      pa.V2 = PB + blk;
-      pa.ldv = n;
-      pa.taus = taus.p;
-      pa.part = part.p;
-      pa.prow = prow.p;
-      pa.barrier = ctx->barrier.p;
-      pa.prof = nullptr;
-      const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, ceil_div(m, rows_target)));
-      pa.rows_per = (int)ceil_div(m, Gp);
-      BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, st));
-      void* kargs[] = {&pa};
-      const size_t smem = (size_t)pa.rows_per * (b + 1) * sizeof(double);
-      BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, st));
-      BK_LAUNCHED(ctx);
-      BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + r0, n, 0.0, S.p, b));
-      sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, st>>>(S.p, taus.p, b, Tk);
-      BK_LAUNCHED(ctx);
-      // ---- T, then the factored panel (rows c0..n: diagonal block, R, V), into every other rank's HBM
-      const double* pan = Aloc.p + c0 + (long long)lb * b * lda;
-      if (others) {
-        BK_TRY(peer_push2d(peer, Tk, b, b, b, vrecv_off[q] + sizeof(double) * panel_elems, b, others, CH_PANEL, seqT, st));
-        BK_TRY(peer_push2d(peer, pan, lda, n - c0, b, vrecv_off[q] + sizeof(double) * c0, n, others, CH_PANEL, seqP, st));
-      }
-      // own deposit (V is already explicit in PA / PB from the QR kernel)
-      dist_unpack_panel_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)(n - c0) * b, 256), 4LL * ctx->sm_count),
-                                 256, 0, st>>>(pan, lda, n, c0, b, Afact, n, PA, PB + blk, n, false);
-      BK_LAUNCHED(ctx);
+      if (factored_ahead)
+        BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+      else
+        BK_TRY(owner_factor(J, PA, PB));
+      factored_ahead = false;
     } else {
-      BK_TRY(peer_wait(peer, CH_PANEL, 1u << owner, seqP, st));
+      BK_TRY(peer_wait(peer, CH_PANEL, 1u << owner, seqP_of(J), st));
       dist_unpack_panel_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)(n - c0) * b, 256), 4LL * ctx->sm_count),
                                  256, 0, st>>>(vrecv + c0, n, n, c0, b, Afact, n, PA, PB + blk, n, true);
       BK_LAUNCHED(ctx);
@@ -766,11 +822,8 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     const int lc0 = lb0 * b;
     const int nact = std::max(0, ncl - lc0);
     const unsigned seqZ = peer_next_seq(peer, CH_ZGATHER);
-    if (stats) BK_CUDA(cudaEventRecord(ev0, st));
-    if (nact > 0)
+    if (nact > 0) {
       BK_TRY(gemm(ctx, true, false, nact, b, m, 1.0, Aloc.p + r0 + (long long)lc0 * lda, lda, VT.p, m, 0.0, Zloc.p, nact));
-    if (stats) {
-      BK_CUDA(cudaEventRecord(ev1, st));
       flops += 2.0 * nact * (double)m * b;
       ++launches;
     }
@@ -794,17 +847,36 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
       dist_gather_rows_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 256), 4LL * ctx->sm_count), 256, 0, st>>>(
           PB, n, nact, lc0, 2 * b, g, G, PBc.p);
       BK_LAUNCHED(ctx);
-      BK_TRY(gemm(ctx, false, true, m, nact, 2 * b, -1.0, PA + r0, n, PBc.p, nact, 1.0, Aloc.p + r0 + (long long)lc0 * lda,
-                  lda));
+      double* C = Aloc.p + r0 + (long long)lc0 * lda;
+      const bool next_is_mine = lookahead && ((J + 1) % G == g) && (n - (r0 + b) >= 2) && nact >= b;
+      if (next_is_mine) {
+        // the next panel is this rank's first active block: update it first, factor it on the side stream under
+        // the rest of the update (QR, T and the pushes of panel J+1 leave the critical path of every rank)
+        BK_TRY(gemm(ctx, false, true, m, b, 2 * b, -1.0, PA + r0, n, PBc.p, nact, 1.0, C, lda));
+        BK_CUDA(cudaEventRecord(e_col, main_st));
+        {
+          BK_CUDA(cudaStreamWaitEvent(side_st, e_col, 0));
+          SideStreamScope sc(ctx);
+          BK_TRY(owner_factor(J + 1, PAbuf.p + (size_t)(q ^ 1) * 2 * blk, PBbuf.p + (size_t)(q ^ 1) * 2 * blk));
+          BK_CUDA(cudaEventRecord(e_fact, side_st));
+        }
+        factored_ahead = true;
+        if (nact > b)
+          BK_TRY(gemm(ctx, false, true, m, nact - b, 2 * b, -1.0, PA + r0, n, PBc.p + b, nact, 1.0, C + (long long)b * lda, lda));
+      } else {
+        BK_TRY(gemm(ctx, false, true, m, nact, 2 * b, -1.0, PA + r0, n, PBc.p, nact, 1.0, C, lda));
+      }
       flops += 2.0 * m * (double)nact * 2 * b;
     }
   }
+  if (factored_ahead) BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+  double* PA = PAbuf.p;
+  double* PB = PBbuf.p;
   // ---- the remaining (unfactored) diagonal blocks reach everyone the same way
   for (; J < nbk; ++J) {
     const int c0 = J * b, owner = J % G, lb = J / G, q = J & 1;
     const int w = std::min(b, n - c0);
-    peer_next_seq(peer, CH_PANEL);
-    const unsigned seqP = peer_next_seq(peer, CH_PANEL);
+    const unsigned seqP = seqP_of(J);
     double* vrecv = peer_ptr(peer, vrecv_off[q]);
     const long long tot = (long long)(n - c0) * w;
     const unsigned nblk = (unsigned)std::min<long long>(ceil_div(tot, 256), 4LL * ctx->sm_count);
@@ -827,12 +899,10 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   BK_TRY(peer_barrier(peer, st));
   BK_TRY(peer_check(peer, st));
   if (stats) {
-    // the Z-product GEMM of the LAST panel only is bracketed (events are re-recorded); the totals are flops
+    // per-rank flops of the Z products and updates; the launches are not bracketed by events in this variant
     stats->gemm_launches = launches;
     stats->gemm_flops = flops;
     stats->gemm_seconds = 0.0;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
   }
   return BK_OK;
 }

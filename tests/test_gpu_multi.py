@@ -1,4 +1,6 @@
-"""Multi-GPU (one process per GPU, NCCL) parity of the row/column-block partitioned fit (GPU, >= 2 devices)."""
+"""Multi-GPU (one process per GPU) parity of the partitioned fit: peer-memory collectives, distributed dense->band
+stage, distributed Krylov K X, sharded predict / cross-validation (GPU, >= 2 devices).  The worker is
+tests/dist_worker.py; its log from `gpurun --gpus 2` / `--gpus 8` is kept under profiles/."""
 import os
 import subprocess
 import sys
@@ -9,13 +11,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_fit_matches_single_gpu():
+def test_multi_rank_fit_matches_oracle():
     import torch
-    if torch.cuda.device_count() < 2:
+    ng = torch.cuda.device_count()
+    if ng < 2:
         pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    nproc = 8 if ng >= 8 else (4 if ng >= 4 else 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py"),
            "nccl"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "DIST_OK" in out.stdout
+    assert "PEER_SELFTEST_OK" in out.stdout and "DIST_OK" in out.stdout
