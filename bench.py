@@ -408,8 +408,8 @@ def main():
         lib.bk_fit_free(h)
         return info.as_dict()
 
-    def e2e_step():
-        fit = bigKRLS(y, X, eigtrunc=EIGTRUNC, comm=comm, pinned=True, ctx=ctx)
+    def e2e_step(pinned=True):
+        fit = bigKRLS(y, X, eigtrunc=EIGTRUNC, comm=comm, pinned=pinned, ctx=ctx)
         d2h = sum(fit[k].nbytes for k in ("K", "vcov.est.c", "vcov.est.fitted", "derivatives", "coeffs", "yfitted")
                   if k in fit) + fit["K.eigenvalues"].nbytes
         fit.release_device()
@@ -438,6 +438,14 @@ def main():
         d2h = e2e_step()
     sync()
     e2e_sec = (time.perf_counter() - t0) / args.steps
+    # the same call into plain PAGEABLE host memory (what a big.matrix is): the library's bounce-buffer copy engine
+    e2e_step(pinned=False)
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step(pinned=False)
+    sync()
+    e2e_pageable_sec = (time.perf_counter() - t0) / args.steps
 
     parity = None
     if N == N_FULL and P == P_FULL:
@@ -445,9 +453,9 @@ def main():
         if comm is not None:
             parity = comm.gather_objects(parity)      # every rank's own column blocks
     if comm is not None:
-        t = torch.tensor([sec, e2e_sec], dtype=torch.float64, device="cuda")
+        t = torch.tensor([sec, e2e_sec, e2e_pageable_sec], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        sec, e2e_sec = t.tolist()
+        sec, e2e_sec, e2e_pageable_sec = t.tolist()
     if rank != 0:
         comm.close()
         torch.distributed.destroy_process_group()
@@ -461,7 +469,7 @@ def main():
         nl = max(1.0, info["band_gemm_launches"])
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_band_gemm_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_band_gemm_traffic.json")))
             traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
         except Exception:  # noqa: BLE001
             pass
@@ -527,7 +535,11 @@ def main():
                        else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "host_buffers": "pinned (library pool)"},
+            "e2e_pageable": {"value": e2e_pageable_sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
+                             "d2h_bytes_per_step": int(d2h),
+                             "host_buffers": "plain pageable numpy memory (big.matrix stand-in), filled by the "
+                                             "library's bounce-buffer copy engine (csrc/hostcopy.cu)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "parity_vs_oracle_fixture": parity,

@@ -113,7 +113,7 @@ double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
     if (!(g < 0.0) || !std::isfinite(f)) break;
     const double xn = x - (f - thr) / g;
     const double nx = (xn > 0.0) ? xn : 0.5 * x;  // Newton from the left of a convex decreasing function stays left
-    if (std::fabs(nx - x) <= 1e-3 * std::max(1.0, std::fabs(x)) * 1e-3) {
+    if (std::fabs(nx - x) <= 5e-3) {  // the candidates are 1 (U) and 0.05 (L) apart: a guess this close is enough
       x = nx;
       break;
     }

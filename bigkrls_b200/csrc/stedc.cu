@@ -682,11 +682,15 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
         p.C = Q.p + lo + (long long)lo * ld;
         probs.push_back(p);
         vec = vec && gemm_operands_vec_ok(p.A, ld, p.B, ld);
-        // bottom rows: Q[mid:hi, lo:lo+K] = G[mid:hi, lo+c1:lo+K] * U[lo+c1:lo+K, lo:lo+K]
+        // bottom rows: Q[mid:hi, lo:lo+K] = G[mid:hi, lo+c1:lo+K] * U[lo+c1:lo+K, lo:lo+K].
+        // When lo + c1 is odd the B operand would start at an odd row and the whole batch would fall back to the
+        // 8-byte operand loads (measured: 7 launches, 50 of the 70 ms of the D&C at N = 20 000).  The contraction may
+        // start one index earlier instead: column lo+c1-1 of G is a type-1 column, exactly zero in the bottom rows.
+        const int back = (((lo + md.c1) & 1) && md.c1 > 0) ? 1 : 0;
         p.m = n2;
-        p.k = md.c2 + md.c3;
-        p.A = Gm.p + md.mid + (long long)(lo + md.c1) * ld;
-        p.B = U.p + (lo + md.c1) + (long long)lo * ld;
+        p.k = md.c2 + md.c3 + back;
+        p.A = Gm.p + md.mid + (long long)(lo + md.c1 - back) * ld;
+        p.B = U.p + (lo + md.c1 - back) + (long long)lo * ld;
         p.C = Q.p + md.mid + (long long)lo * ld;
         probs.push_back(p);
         vec = vec && gemm_operands_vec_ok(p.A, ld, p.B, ld);

@@ -144,3 +144,31 @@ def test_lambda_bounds_bisection_equals_linear_scan(seed):
 def test_lambda_bounds_degenerate_spectrum_is_an_error():
     rc, _, _ = host_bounds(np.zeros(50), 50)           # sum(ev/(ev+U)) < 1 for every U: the scan never ends
     assert rc != 0
+
+
+def test_user_supplied_bounds_are_respected_including_zero():
+    """R accepts L = 0 (`L >= 0`, R/bigKRLS.R:225-228): a supplied bound is used as is, only a missing one (L < 0 /
+    U <= 0 at the C boundary) triggers the reference's bounds loop."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n = 400
+    ev = np.sort(n / (1.0 + np.arange(n)) ** 1.5)[::-1]
+    ev *= n / ev.sum()
+
+    def cb(user, lams, nlam, out):
+        for i in range(nlam):
+            out[i] = (lams[i] - 3.0) ** 2 * 100.0      # convex, minimum at 3
+        return 0
+
+    cbf = _lib.LE_CALLBACK(cb)
+    out = {}
+    for name, (L, U) in {"both": (0.0, 10.0), "auto": (-1.0, 0.0)}.items():
+        lam, Lo, Uo = C.c_double(), C.c_double(), C.c_double()
+        probes, passes = C.c_int(), C.c_int()
+        evc = np.ascontiguousarray(ev)
+        _lib.check(lib.bk_host_lambda_search(_lib.dptr(evc), n, n, L, U, 0.0, 7, C.cast(cbf, C.c_void_p), None,
+                                             C.byref(lam), C.byref(Lo), C.byref(Uo), C.byref(probes), C.byref(passes)))
+        out[name] = (lam.value, Lo.value, Uo.value)
+    assert out["both"][1:] == (0.0, 10.0) and abs(out["both"][0] - 3.0) < 0.5
+    L0, U0 = o.lambda_bounds(ev, n)
+    assert out["auto"][1:] == (L0, U0)

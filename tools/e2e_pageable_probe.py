@@ -11,8 +11,17 @@ ctx = _lib.default_context(0)
 def shm_alloc(name, shape):
     path = "/dev/shm/bk_%s_%d.bin" % (name.replace(".", "_"), os.getpid())
     return np.memmap(path, dtype=np.float64, mode="w+", shape=shape, order="F")
+_pre = {}
+def shm_prefaulted(name, shape):
+    """The reference's R wrappers allocate every output big.matrix with init = 0 before the native call
+    (R/bigKRLS_Rcpp_functions.R:206,235,251): the pages exist when the library writes into them."""
+    if name not in _pre:
+        _pre[name] = shm_alloc("pre_" + name, shape)
+        _pre[name][:] = 0.0
+    return _pre[name]
 res = {}
-for label, kw in (("pinned", dict(pinned=True)), ("pageable", dict()), ("shm_memmap", dict(squares_alloc=shm_alloc))):
+for label, kw in (("pinned", dict(pinned=True)), ("pageable", dict()), ("shm_memmap", dict(squares_alloc=shm_alloc)),
+                  ("shm_memmap_prefaulted", dict(squares_alloc=shm_prefaulted))):
     ts = []
     for rep in range(3):
         t0 = time.perf_counter()
