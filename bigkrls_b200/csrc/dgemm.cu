@@ -27,7 +27,7 @@
 namespace bk {
 
 static constexpr int BK = 16;
-static constexpr int STAGES = 3;
+static constexpr int kStages = 3;  // default pipeline depth (template parameter STAGES of the kernel)
 static constexpr int KPAD = BK + 4;  // K-major row stride (doubles), 20 = 4 mod 16
 
 template <int BMN>
@@ -92,8 +92,8 @@ __device__ __forceinline__ void load_k_major(double* dst, const double* __restri
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC>
-__global__ void __launch_bounds__(WM* WN * 32)
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC, int STAGES = 3, bool PFC = false>
+__global__ void __launch_bounds__(WM* WN * 32, PFC ? 3 : 0)
     dgemm_kernel(const GemmProb single, const GemmProb* __restrict__ probs, int splits,
                  double* __restrict__ ws) {
   constexpr int NT = WM * WN * 32;
@@ -111,6 +111,17 @@ __global__ void __launch_bounds__(WM* WN * 32)
   const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
   const int m0 = tm * BM, n0 = tn * BN;
   if (pr.lower && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
+  // Phase stagger: the CTAs that share an SM start together and, all tiles being equal, stay in lock-step - they
+  // reach the epilogue (no DMMA) at the same time and the tensor pipe idles.  Delaying the 2nd / 3rd resident CTA of
+  // the first wave by a fraction of a tile time de-phases them once; their successors inherit the offset.
+  if (pr.stagger > 0) {
+    const unsigned wave = (blockIdx.x + gridDim.x * blockIdx.y) / (unsigned)pr.stagger_sms;
+    if (wave > 0 && wave < (unsigned)pr.stagger_slots) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)wave * pr.stagger) {
+      }
+    }
+  }
 
   // split-K range (multiples of BK)
   int kbeg = 0, kend = pr.k;
@@ -131,6 +142,23 @@ __global__ void __launch_bounds__(WM* WN * 32)
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // Read-modify-write updates (beta != 0) on 64 x 64 tiles: the C tile is fetched into registers NOW, so that its HBM
+  // latency is hidden under the main loop instead of being exposed in the epilogue of every tile (the short-k
+  // rank-128 / rank-256 updates of the dense->band stage spend a quarter of a tile's time there).
+  constexpr bool kPrefetchC = PFC && (BM == 64 && BN == 64);
+  constexpr int NPRE = kPrefetchC ? (BM / 2) * BN / NT : 1;
+  double2 cpre[NPRE];
+  const bool vecC0 = ((((uintptr_t)pr.C) & 15u) == 0) && (pr.ldc % 2 == 0);
+  const bool pre_ok = kPrefetchC && pr.prefetch_c && splits == 1 && pr.beta != 0.0 && vecC0 && (m0 + BM <= pr.m) && (n0 + BN <= pr.n);
+  if (pre_ok) {
+#pragma unroll
+    for (int it = 0; it < NPRE; ++it) {
+      const int idx = threadIdx.x + it * NT;
+      const int rp = idx % (BM / 2), cc = idx / (BM / 2);
+      cpre[it] = *reinterpret_cast<const double2*>(pr.C + (m0 + 2 * rp) + (long long)(n0 + cc) * pr.ldc);
+    }
+  }
 
   auto load_stage = [&](int stage, int kt) {
     const int k0 = kbeg + kt * BK;
@@ -216,7 +244,8 @@ __global__ void __launch_bounds__(WM* WN * 32)
             Cs[(wn0 - c_lo + j * 8 + 2 * t + e) * LDS + wm0 + i * 8 + g] = acc[i][j][e];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < (BM / 2) * CW; idx += NT) {
+    int pre_it = 0;
+    for (int idx = threadIdx.x; idx < (BM / 2) * CW; idx += NT, ++pre_it) {
       const int rp = idx % (BM / 2), cc = idx / (BM / 2);
       const int row = m0 + 2 * rp, col = n0 + c_lo + cc;
       if (row >= pr.m || col >= pr.n) continue;
@@ -225,7 +254,7 @@ __global__ void __launch_bounds__(WM* WN * 32)
       if (vecC && row + 1 < pr.m) {
         double2 o = make_double2(v0, v1);
         if (beta != 0.0) {
-          const double2 old = *reinterpret_cast<const double2*>(cp);
+          const double2 old = pre_ok ? cpre[kPrefetchC ? pre_it : 0] : *reinterpret_cast<const double2*>(cp);
           o.x += beta * old.x;
           o.y += beta * old.y;
         }
@@ -246,6 +275,8 @@ __global__ void __launch_bounds__(WM* WN * 32)
     if (mirror) {
       // transposed copy of the finished tile: C[col, row], contiguous along the tile's columns
       __syncthreads();
+      // (16-byte mirror stores - two tile columns per thread - were measured slower: 27.2 against 28.0 TF at k = 256;
+      //  the strided shared-memory reads they need conflict two-way)
       for (int idx = threadIdx.x; idx < BM * CW; idx += NT) {
         const int cc = idx % CW, rr = idx / CW;
         const int row = m0 + rr, col = n0 + c_lo + cc;
@@ -270,16 +301,16 @@ __global__ void splitk_reduce_kernel(GemmProb pr, int splits, const double* __re
   }
 }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int ST = kStages>
 static size_t smem_bytes() {
-  return (size_t)STAGES * (TileSize<BM>::max + TileSize<BN>::max) * sizeof(double);
+  return (size_t)ST * (TileSize<BM>::max + TileSize<BN>::max) * sizeof(double);
 }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC>
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool VEC, int ST = kStages, bool PFC = false>
 static int launch_one(bk_ctx* ctx, const GemmProb& single, const GemmProb* dprobs, int nprob,
                       int max_tiles, int splits, double* ws) {
-  auto kern = dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC>;
-  const size_t smem = smem_bytes<BM, BN, WM, WN>();
+  auto kern = dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC, ST, PFC>;
+  const size_t smem = smem_bytes<BM, BN, WM, WN, ST>();
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -352,6 +383,11 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
   p.beta = beta;
   p.lower = lower;
   const bool vec = gemm_operands_vec_ok(A, lda, B, ldb);
+  p.stagger = 0;
+  static const bool no_prefetch = getenv("BK_GEMM_NOPREFETCH") != nullptr;
+  p.prefetch_c = no_prefetch ? 0 : 1;
+  p.stagger_sms = ctx->sm_count;
+  p.stagger_slots = 0;
 
   int bm, bn;
   if (n <= 32) {
@@ -407,8 +443,23 @@ int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const
     BK_TRY(ctx->gemm_ws.ensure((size_t)splits * (size_t)m * (size_t)n));
     ws = ctx->gemm_ws.p;
   }
+  {
+    // start stagger of the first wave (see the kernel): only for grids of many equal tiles
+    static const int stagger_cycles = getenv("BK_GEMM_STAGGER") ? atoi(getenv("BK_GEMM_STAGGER")) : 0;
+    if (stagger_cycles > 0 && (long long)tiles * splits > 4LL * slots) {
+      p.stagger = stagger_cycles;
+      p.stagger_slots = resident;
+    }
+  }
   int rc;
-  if (bn == 32)
+  // Short read-modify-write updates (k <= 128, the rank-128 updates of the distributed / un-paired dense->band stage):
+  // the variant that fetches the C tile into registers before the main loop (24.1 against 22.8 TF at k = 128; at
+  // k = 256 the extra 16 registers cost more than the hidden latency gains: 27.4 against 28.0 TF).
+  // (Also measured and dropped: a 2-stage pipeline with 4 CTAs per SM, 26.6 against 28.0 TF; a start stagger of the
+  // first wave, no effect - the CTAs of an SM are not phase-locked.)
+  if (bm == 64 && bn == 64 && !ta && tb && vec && splits == 1 && beta != 0.0 && k <= 128 && p.prefetch_c)
+    rc = launch_one<64, 64, 2, 4, false, true, true, 3, true>(ctx, p, nullptr, 1, tiles, splits, ws);
+  else if (bn == 32)
     rc = dispatch<128, 32, 8, 1>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
   else if (bm == 128 && bn == 64)
     rc = dispatch<128, 64, 4, 2>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);

@@ -11,6 +11,10 @@ struct GemmProb {
   int m, n, k;
   long long lda, ldb, ldc;
   double alpha, beta;
+  int stagger = 0;        // cycles of start delay per resident-slot index for the CTAs of the FIRST wave (0 = none)
+  int stagger_sms = 1;    // SMs of the device (CTA id / stagger_sms = slot index of a first-wave CTA)
+  int stagger_slots = 0;  // resident CTAs per SM
+  int prefetch_c = 1;     // 64 x 64 read-modify-write tiles: fetch the C tile into registers before the main loop
   int lower;  // 1: tiles strictly above the diagonal are skipped (symmetric / SYR2K-like updates);
               // 2: as 1, and every tile strictly below the diagonal is also written transposed (full symmetric C)
 };

@@ -100,9 +100,10 @@ struct TopkStats {
   int restarts = 0, matvecs = 0, block = 0, basis = 0;
   double residual = 0;
 };
-// With `peer`: K is this rank's column block K[:, c0:c0+nloc] and the K X products are distributed (collective, every
-// rank returns the same values and vectors).
-size_t eigen_topk_heap_bytes(int n);
+// With `peer`: K is this rank's column block K[:, c0:c0+nloc] and EVERYTHING n-long (basis, K X, residuals) is
+// row-partitioned over the ranks; the small projected matrices are all-reduced in a fixed rank order (collective,
+// every rank returns the same values and the full set of vectors).
+size_t eigen_topk_heap_bytes(int n, int k);
 int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
                long long ldz, TopkStats* stats, bk_peer* peer = nullptr, int c0 = 0, int nloc = 0);
 // policy shared by bk_eigen and the fused fit

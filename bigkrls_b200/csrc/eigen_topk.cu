@@ -22,20 +22,24 @@
 
 namespace bk {
 
-__global__ void hash_fill_kernel(double* p, long long n, unsigned long long seed) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    unsigned long long x = (unsigned long long)i * 6364136223846793005ULL + seed;
+// p[i + j*ld] for local rows i of a matrix whose GLOBAL row index is row0 + i (n_glob rows in total): the value
+// depends only on the global position, so a row-partitioned start block is the same matrix for any number of ranks
+__global__ void hash_fill_kernel(double* p, int rows, int cols, long long ld, int row0, int n_glob, unsigned long long seed) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % rows), j = (int)(idx / rows);
+    unsigned long long x = (unsigned long long)((long long)(row0 + i) + (long long)j * n_glob) * 6364136223846793005ULL + seed;
     x ^= x >> 33;
     x *= 0xff51afd7ed558ccdULL;
     x ^= x >> 33;
     x *= 0xc4ceb9fe1a85ec53ULL;
     x ^= x >> 33;
-    p[i] = (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    p[i + (long long)j * ld] = (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
   }
 }
 
-// R[:, j] = KQ[:, j] - theta[j] * Q[:, j];  nrm2[j] = ||R[:, j]||^2   (one CTA per column)
+// R[:, j] = KQ[:, j] - theta[j] * Q[:, j];  nrm2[j] = ||R[:, j]||^2 over the local rows   (one CTA per column)
 __global__ void ritz_residual_kernel(const double* __restrict__ Q, const double* __restrict__ KQ,
                                      const double* __restrict__ theta, int n, double* __restrict__ R,
                                      double* __restrict__ nrm2) {
@@ -54,25 +58,38 @@ __global__ void ritz_residual_kernel(const double* __restrict__ Q, const double*
 
 namespace {
 
+// Everything n-long is ROW-PARTITIONED over the ranks of the peer communicator (nl local rows starting at global
+// row c0; single GPU: nl = n): products of the form A'B over the long dimension are local partial sums followed by
+// an all-reduce that adds the ranks in a fixed order, so every rank holds the same small matrices bit for bit and
+// takes the same decisions; A * (small) products are local.
 struct Ws {
   bk_ctx* ctx;
-  int n;
+  bk_peer* peer;
+  int n, nl, c0;
+  size_t stage_off;       // large all-reduce staging in the symmetric heap
+  long long slot_elems;
   DevBuf<double> G, Gs, T1, T2, scale;
+  int allreduce(double* buf, long long cnt) {
+    if (!peer) return BK_OK;
+    if (cnt <= 4096) return peer_allreduce_sum(peer, buf, cnt, ctx->stream);
+    return peer_allreduce_sum_large(peer, buf, cnt, stage_off, slot_elems, ctx->stream);
+  }
 };
 
-// X (n x b, ld n) <- orthonormal basis of its span via the eigen-decomposition of the Gram matrix,
+// X (nl x b local rows, ld nl) <- orthonormal basis of its span via the eigen-decomposition of the Gram matrix,
 // applied twice.  Returns the number of columns kept (directions with relative Gram eigenvalue below
 // `drop` are discarded - Krylov breakdown / rank deficiency).
 int orth_gram(Ws& w, double* X, int b, int* kept) {
   bk_ctx* ctx = w.ctx;
-  const int n = w.n;
+  const int nl = w.nl;
   int r = b;
   for (int pass = 0; pass < 2 && r > 0; ++pass) {
     BK_TRY(w.G.ensure((size_t)r * r));
     BK_TRY(w.Gs.ensure((size_t)r * r));
-    BK_TRY(w.T1.ensure((size_t)n * r));
+    BK_TRY(w.T1.ensure((size_t)nl * r));
     BK_TRY(w.scale.ensure(r));
-    BK_TRY(gemm(ctx, true, false, r, r, n, 1.0, X, n, X, n, 0.0, w.G.p, r));
+    BK_TRY(gemm(ctx, true, false, r, r, nl, 1.0, X, nl, X, nl, 0.0, w.G.p, r));
+    BK_TRY(w.allreduce(w.G.p, (long long)r * r));
     std::vector<double> ev(r);
     int nw = 0;
     BK_TRY(eigen_full(ctx, w.G.p, r, r, ev.data(), r, -INFINITY, &nw, w.Gs.p, r, nullptr));
@@ -91,8 +108,8 @@ int orth_gram(Ws& w, double* X, int b, int* kept) {
     }
     BK_CUDA(cudaMemcpyAsync(w.scale.p, sc.data(), sizeof(double) * keep, cudaMemcpyHostToDevice, ctx->stream));
     BK_TRY(col_scale(ctx, w.Gs.p, r, r, keep, w.scale.p, nullptr, w.Gs.p, r));
-    BK_TRY(gemm(ctx, false, false, n, keep, r, 1.0, X, n, w.Gs.p, r, 0.0, w.T1.p, n));
-    BK_TRY(copy_matrix(ctx, w.T1.p, n, n, keep, 1.0, X, n));
+    BK_TRY(gemm(ctx, false, false, nl, keep, r, 1.0, X, nl, w.Gs.p, r, 0.0, w.T1.p, nl));
+    BK_TRY(copy_matrix(ctx, w.T1.p, nl, nl, keep, 1.0, X, nl));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));  // sc / ev are host temporaries
     r = keep;
   }
@@ -100,68 +117,79 @@ int orth_gram(Ws& w, double* X, int b, int* kept) {
   return BK_OK;
 }
 
-// W (n x b) -= V (V' W), twice (classical Gram-Schmidt with re-orthogonalisation)
+// W (nl x b) -= V (V' W), twice (classical Gram-Schmidt with re-orthogonalisation)
 int project_out(Ws& w, const double* V, int m, double* W, int b) {
   if (m <= 0 || b <= 0) return BK_OK;
   BK_TRY(w.T2.ensure((size_t)m * b));
   for (int pass = 0; pass < 2; ++pass) {
-    BK_TRY(gemm(w.ctx, true, false, m, b, w.n, 1.0, V, w.n, W, w.n, 0.0, w.T2.p, m));
-    BK_TRY(gemm(w.ctx, false, false, w.n, b, m, -1.0, V, w.n, w.T2.p, m, 1.0, W, w.n));
+    BK_TRY(gemm(w.ctx, true, false, m, b, w.nl, 1.0, V, w.nl, W, w.nl, 0.0, w.T2.p, m));
+    BK_TRY(w.allreduce(w.T2.p, (long long)m * b));
+    BK_TRY(gemm(w.ctx, false, false, w.nl, b, m, -1.0, V, w.nl, w.T2.p, m, 1.0, W, w.nl));
   }
   return BK_OK;
 }
 
 }  // namespace
 
-size_t eigen_topk_heap_bytes(int n) { return sizeof(double) * 2 * (size_t)n * 128 + 4096; }
+size_t eigen_topk_heap_bytes(int n, int k) {
+  const int b = std::min(128, std::max(8, std::min(n, (k + 3) / 4)));
+  const long long m_max = std::min<long long>(n, (long long)k + 8 * b);
+  // gathered X block (2 x n x 128), staging of the large all-reduce (2 parities x 8 slots x m_max^2), gathered result
+  return sizeof(double) * (2 * (size_t)n * 128 + 2 * 8 * (size_t)(m_max * m_max + 64) + (size_t)n * k) + 16384;
+}
 
 int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double* evals_host, double* Z,
                long long ldz, TopkStats* stats, bk_peer* peer, int c0, int nloc) {
   BK_REQUIRE(k >= 1 && k <= n, "eigen_topk: k must be in 1..n");
-  // K X.  Single GPU: one GEMM over the whole K.  With a peer communicator K stays PARTITIONED: `K` is this rank's
-  // column block K[:, c0:c0+nloc] (= its row panel, K is symmetric), the rank forms its rows of K X and stores them
-  // into every other rank's copy of the block over NVLink (one all-gather of n x b per product); the rest of the
-  // iteration (orthogonalisation, Rayleigh-Ritz) is replicated and bit-identical on every rank.
-  size_t y_off[2] = {0, 0};
+  const int b = std::min(128, std::max(8, std::min(n, (k + 3) / 4)));
+  const int m_max = std::min(n, k + 8 * b);
+  const double tol = 2e-13;
+  const int nl = peer ? nloc : n;      // local rows
+  const int r0 = peer ? c0 : 0;
+  Ws w;
+  w.ctx = ctx;
+  w.peer = peer;
+  w.n = n;
+  w.nl = nl;
+  w.c0 = r0;
+  w.stage_off = 0;
+  w.slot_elems = (long long)m_max * m_max + 64;
+  // K X.  Single GPU: one GEMM over the whole K.  With a peer communicator K stays PARTITIONED (`K` is this rank's
+  // column block K[:, c0:c0+nloc] = its row panel, K is symmetric): the rows of X are gathered from all ranks into a
+  // symmetric buffer by peer stores over NVLink, and K[:, own]' X gives this rank's rows of K X.
+  size_t x_off[2] = {0, 0}, z_off = 0;
   unsigned mv_count = 0;
   if (peer) {
-    for (int q = 0; q < 2; ++q) BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * 128, &y_off[q]));
+    for (int q = 0; q < 2; ++q) BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * 128, &x_off[q]));
+    BK_TRY(peer_alloc(peer, sizeof(double) * 2 * (size_t)peer->world * (size_t)w.slot_elems, &w.stage_off));
+    BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * k, &z_off));
     BK_TRY(peer_barrier(peer, ctx->stream));
   }
   auto matvec = [&](const double* X, int bx, double* KX) -> int {
     if (!peer) return gemm(ctx, false, false, n, bx, n, 1.0, K, ldk, X, n, 0.0, KX, n);
     const int q = (int)(mv_count++ & 1u);
-    double* Y = peer_ptr(peer, y_off[q]);
-    const unsigned others = ((1u << peer->world) - 1u) & ~(1u << peer->rank);
-    BK_TRY(gemm(ctx, true, false, nloc, bx, n, 1.0, K, ldk, X, n, 0.0, Y + c0, n));
+    const unsigned all = (1u << peer->world) - 1u;
     const unsigned seq = peer_next_seq(peer, CH_KRYLOV);
-    BK_TRY(peer_push2d(peer, Y + c0, n, nloc, bx, y_off[q] + sizeof(double) * (size_t)c0, n, others, CH_KRYLOV, seq,
-                       ctx->stream));
-    BK_TRY(peer_wait(peer, CH_KRYLOV, others, seq, ctx->stream));
-    return copy_matrix(ctx, Y, n, n, bx, 1.0, KX, n);
+    BK_TRY(peer_push2d(peer, X, nl, nl, bx, x_off[q] + sizeof(double) * (size_t)r0, n, all, CH_KRYLOV, seq, ctx->stream));
+    BK_TRY(peer_wait(peer, CH_KRYLOV, all, seq, ctx->stream));
+    return gemm(ctx, true, false, nl, bx, n, 1.0, K, ldk, peer_ptr(peer, x_off[q]), n, 0.0, KX, nl);
   };
-  const int b = std::min(128, std::max(8, std::min(n, (k + 3) / 4)));
-  const int m_max = std::min(n, k + 8 * b);
-  const double tol = 2e-13;
-  Ws w;
-  w.ctx = ctx;
-  w.n = n;
   DevBuf<double> V, KV, Wt, Qb, KQb, H, S, theta_d, nrm_d, Rb;
   DevBuf<int> idx_d;
-  BK_TRY(V.alloc((size_t)n * (m_max + b)));
-  BK_TRY(KV.alloc((size_t)n * (m_max + b)));
-  BK_TRY(Wt.alloc((size_t)n * b));
-  BK_TRY(Qb.alloc((size_t)n * k));
-  BK_TRY(KQb.alloc((size_t)n * k));
-  BK_TRY(Rb.alloc((size_t)n * k));
+  BK_TRY(V.alloc((size_t)nl * (m_max + b)));
+  BK_TRY(KV.alloc((size_t)nl * (m_max + b)));
+  BK_TRY(Wt.alloc((size_t)nl * b));
+  BK_TRY(Qb.alloc((size_t)nl * k));
+  BK_TRY(KQb.alloc((size_t)nl * k));
+  BK_TRY(Rb.alloc((size_t)nl * k));
   BK_TRY(H.alloc((size_t)m_max * m_max));
   BK_TRY(S.alloc((size_t)m_max * k));
   BK_TRY(theta_d.alloc(k));
   BK_TRY(nrm_d.alloc(k));
   BK_TRY(idx_d.alloc(b));
 
-  // deterministic pseudo-random start block
-  hash_fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(V.p, (long long)n * b, 0x9E3779B97F4A7C15ULL);
+  // deterministic pseudo-random start block (a function of the global position only)
+  hash_fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(V.p, nl, b, nl, r0, n, 0x9E3779B97F4A7C15ULL);
   BK_LAUNCHED(ctx);
   int bx = 0;
   BK_TRY(orth_gram(w, V.p, b, &bx));
@@ -172,17 +200,17 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
   for (; outer < max_outer; ++outer) {
     // ---- expand the Krylov basis ------------------------------------------------------------------
     while (bx > 0 && m + bx <= m_max) {
-      double* X = V.p + (size_t)m * n;
-      double* KX = KV.p + (size_t)m * n;
+      double* X = V.p + (size_t)m * nl;
+      double* KX = KV.p + (size_t)m * nl;
       BK_TRY(matvec(X, bx, KX));
       matvecs += bx;
       m += bx;
-      BK_TRY(copy_matrix(ctx, KX, n, n, bx, 1.0, Wt.p, n));
+      BK_TRY(copy_matrix(ctx, KX, nl, nl, bx, 1.0, Wt.p, nl));
       BK_TRY(project_out(w, V.p, m, Wt.p, bx));
       int r = 0;
       BK_TRY(orth_gram(w, Wt.p, bx, &r));
       bx = r;
-      if (bx > 0 && m + bx <= m_max + b) BK_TRY(copy_matrix(ctx, Wt.p, n, n, bx, 1.0, V.p + (size_t)m * n, n));
+      if (bx > 0 && m + bx <= m_max + b) BK_TRY(copy_matrix(ctx, Wt.p, nl, nl, bx, 1.0, V.p + (size_t)m * nl, nl));
       if (m + bx > m_max) break;
     }
     if (m < k) {
@@ -191,16 +219,18 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
       return BK_ERR_NUMERIC;
     }
     // ---- Rayleigh-Ritz -----------------------------------------------------------------------------
-    BK_TRY(gemm(ctx, true, false, m, m, n, 1.0, V.p, n, KV.p, n, 0.0, H.p, m));
+    BK_TRY(gemm(ctx, true, false, m, m, nl, 1.0, V.p, nl, KV.p, nl, 0.0, H.p, m));
+    BK_TRY(w.allreduce(H.p, (long long)m * m));
     std::vector<double> ev(m);
     int nw = 0;
     BK_TRY(eigen_full(ctx, H.p, m, m, ev.data(), k, -INFINITY, &nw, S.p, m, nullptr));
     for (int j = 0; j < k; ++j) th[j] = ev[j];
     BK_CUDA(cudaMemcpyAsync(theta_d.p, th.data(), sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
-    BK_TRY(gemm(ctx, false, false, n, k, m, 1.0, V.p, n, S.p, m, 0.0, Qb.p, n));
-    BK_TRY(gemm(ctx, false, false, n, k, m, 1.0, KV.p, n, S.p, m, 0.0, KQb.p, n));
-    ritz_residual_kernel<<<k, 256, 0, ctx->stream>>>(Qb.p, KQb.p, theta_d.p, n, Rb.p, nrm_d.p);
+    BK_TRY(gemm(ctx, false, false, nl, k, m, 1.0, V.p, nl, S.p, m, 0.0, Qb.p, nl));
+    BK_TRY(gemm(ctx, false, false, nl, k, m, 1.0, KV.p, nl, S.p, m, 0.0, KQb.p, nl));
+    ritz_residual_kernel<<<k, 256, 0, ctx->stream>>>(Qb.p, KQb.p, theta_d.p, nl, Rb.p, nrm_d.p);
     BK_LAUNCHED(ctx);
+    BK_TRY(w.allreduce(nrm_d.p, k));
     BK_CUDA(cudaMemcpyAsync(nrm.data(), nrm_d.p, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
     double worst = 0.0;
@@ -216,14 +246,14 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
     std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return nrm[a] > nrm[c]; });
     const int nb = std::min(b, k);
     BK_CUDA(cudaMemcpyAsync(idx_d.p, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-    BK_TRY(gather_columns(ctx, Rb.p, n, n, nb, idx_d.p, Wt.p, n));
+    BK_TRY(gather_columns(ctx, Rb.p, nl, nl, nb, idx_d.p, Wt.p, nl));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, V.p, n));
-    BK_TRY(copy_matrix(ctx, KQb.p, n, n, k, 1.0, KV.p, n));
+    BK_TRY(copy_matrix(ctx, Qb.p, nl, nl, k, 1.0, V.p, nl));
+    BK_TRY(copy_matrix(ctx, KQb.p, nl, nl, k, 1.0, KV.p, nl));
     m = k;
     BK_TRY(project_out(w, V.p, m, Wt.p, nb));
     BK_TRY(orth_gram(w, Wt.p, nb, &bx));
-    if (bx > 0) BK_TRY(copy_matrix(ctx, Wt.p, n, n, bx, 1.0, V.p + (size_t)m * n, n));
+    if (bx > 0) BK_TRY(copy_matrix(ctx, Wt.p, nl, nl, bx, 1.0, V.p + (size_t)m * nl, nl));
     if (bx == 0) break;  // residuals vanish numerically: converged as far as FP64 goes
   }
   double worst = 0.0;
@@ -234,7 +264,18 @@ int eigen_topk(bk_ctx* ctx, const double* K, long long ldk, int n, int k, double
     return BK_ERR_NUMERIC;
   }
   for (int j = 0; j < k; ++j) evals_host[j] = th[j];
-  if (Z) BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, Z, ldz));
+  if (Z) {
+    if (!peer) {
+      BK_TRY(copy_matrix(ctx, Qb.p, n, n, k, 1.0, Z, ldz));
+    } else {
+      // every rank needs all rows of the eigenvectors: all-gather of the row panels by peer stores
+      const unsigned all = (1u << peer->world) - 1u;
+      const unsigned seq = peer_next_seq(peer, CH_KRYLOV);
+      BK_TRY(peer_push2d(peer, Qb.p, nl, nl, k, z_off + sizeof(double) * (size_t)r0, n, all, CH_KRYLOV, seq, ctx->stream));
+      BK_TRY(peer_wait(peer, CH_KRYLOV, all, seq, ctx->stream));
+      BK_TRY(copy_matrix(ctx, peer_ptr(peer, z_off), n, n, k, 1.0, Z, ldz));
+    }
+  }
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (peer) {
     BK_TRY(peer_barrier(peer, ctx->stream));

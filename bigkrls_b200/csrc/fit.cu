@@ -381,7 +381,7 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
     size_t need = sizeof(double) * ((size_t)f->neig + 16 + (size_t)n * (topk ? 0 : f->neig) + (size_t)n +
                                     (size_t)n * std::max(1, pd_all)) + 8192;
     need += dist_eig ? sy2sb_dist_heap_bytes(n) : 0;
-    need += topk ? eigen_topk_heap_bytes(n) : 0;
+    need += topk ? eigen_topk_heap_bytes(n, f->neig) : 0;
     BK_TRY(peer_ensure_heap(peer, need));
     BK_TRY(peer_alloc(peer, sizeof(double) * ((size_t)f->neig + 16), &off_pack));
     if (!topk) BK_TRY(peer_alloc(peer, sizeof(double) * (size_t)n * f->neig, &off_Q));

@@ -60,7 +60,7 @@ struct HostCopier {
     bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
       ok = cudaHostAlloc((void**)&bounce[i], CHUNK, cudaHostAllocDefault) == cudaSuccess &&
-           cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     }
     if (!ok) {
       // this lane cannot work (no pinned memory left?): leave; copier_submit falls back to a plain copy once

@@ -99,6 +99,16 @@ int push1d(bk_peer* p, const double* src, long long n, size_t dst_off, unsigned 
   return BK_OK;
 }
 
+__global__ void __launch_bounds__(256) peer_sum_slots_kernel(PeerDev pd, double* __restrict__ buf, long long n, size_t base,
+                                                             long long slot_elems) {
+  const double* mine = reinterpret_cast<const double*>(pd.heap[pd.rank] + base);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < pd.world; ++r) s += __ldcg(mine + (long long)r * slot_elems + i);
+    buf[i] = s;
+  }
+}
+
 int open_heaps(bk_peer* p, size_t bytes) {
   // own heap + IPC handle exchange (host-side collective through the bootstrap callback)
   char* mine = nullptr;
@@ -168,6 +178,7 @@ int peer_ensure_heap(bk_peer* p, size_t bytes) {
   // the flags restart from zero with the new heaps
   memset(p->seq, 0, sizeof(p->seq));
   p->ar_count = 0;
+  p->arl_count = 0;
   return open_heaps(p, bytes);
 }
 
@@ -204,6 +215,21 @@ int peer_allreduce_sum(bk_peer* p, double* buf, long long n, cudaStream_t st) {
     peer_allreduce_kernel<<<1, 1024, 0, st>>>(p->dev, buf + o, cnt, (int)(p->ar_count++ & 1u), seq);
     BK_LAUNCHED(p->ctx);
   }
+  BK_CUDA(cudaGetLastError());
+  return BK_OK;
+}
+
+int peer_allreduce_sum_large(bk_peer* p, double* buf, long long n, size_t stage_off, long long slot_elems, cudaStream_t st) {
+  if (n <= 0) return BK_OK;
+  const unsigned all = (1u << p->world) - 1u;
+  const int q = (int)(p->arl_count++ & 1u);
+  const size_t base = stage_off + sizeof(double) * (size_t)q * (size_t)p->world * (size_t)slot_elems;
+  const unsigned seq = peer_next_seq(p, CH_ARLARGE);
+  BK_TRY(push1d(p, buf, n, base + sizeof(double) * (size_t)p->rank * (size_t)slot_elems, all, CH_ARLARGE, seq, st));
+  BK_TRY(peer_wait(p, CH_ARLARGE, all, seq, st));
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(n, 512), 4LL * p->ctx->sm_count));
+  peer_sum_slots_kernel<<<blocks, 256, 0, st>>>(p->dev, buf, n, base, slot_elems);
+  BK_LAUNCHED(p->ctx);
   BK_CUDA(cudaGetLastError());
   return BK_OK;
 }

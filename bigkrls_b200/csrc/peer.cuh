@@ -28,7 +28,7 @@ static constexpr int PEER_AR_MAX = 32768;
 static constexpr size_t PEER_CTRL_BYTES = 8u << 20;
 
 // channels (each has its own monotone sequence counter)
-enum PeerChannel { CH_COLL = 0, CH_BARRIER = 1, CH_PANEL = 2, CH_ZGATHER = 3, CH_KRYLOV = 4, CH_GATHER = 5, CH_BCAST = 6 };
+enum PeerChannel { CH_COLL = 0, CH_BARRIER = 1, CH_PANEL = 2, CH_ZGATHER = 3, CH_KRYLOV = 4, CH_GATHER = 5, CH_BCAST = 6, CH_ARLARGE = 7 };
 
 }  // namespace bk
 
@@ -42,6 +42,7 @@ struct bk_peer {
   size_t bump = 0;                       // next free offset (>= PEER_CTRL_BYTES)
   unsigned seq[bk::PEER_CHANNELS] = {};  // last sequence number used per channel (same on every rank)
   unsigned ar_count = 0;                 // all-reduce staging parity
+  unsigned arl_count = 0;                // the same for the large all-reduce
 };
 
 namespace bk {
@@ -58,6 +59,10 @@ inline double* peer_ptr(bk_peer* p, size_t off) { return reinterpret_cast<double
 int peer_barrier(bk_peer* p, cudaStream_t st);
 // in-place sum over ranks of n doubles at `buf` (any device pointer); identical bits on every rank
 int peer_allreduce_sum(bk_peer* p, double* buf, long long n, cudaStream_t st);
+// the same for long vectors (multi-CTA): every rank stores its vector into slot [parity][rank] of the staging area at
+// heap offset stage_off on every rank (2 x world x slot_elems doubles, slot_elems >= n), waits for all, adds the
+// slots in rank order
+int peer_allreduce_sum_large(bk_peer* p, double* buf, long long n, size_t stage_off, long long slot_elems, cudaStream_t st);
 // every rank owns the segment [displs[r], displs[r]+counts[r]) (doubles) of the symmetric buffer at heap offset
 // `off`; afterwards every rank holds all segments
 int peer_allgatherv_sym(bk_peer* p, size_t off, const long long* counts, const long long* displs, cudaStream_t st);

@@ -27,6 +27,11 @@ namespace bk {
 
 static constexpr int SB = 64;     // bandwidth / panel width
 static constexpr int QR_NT = 256;
+// CTAs of the cooperative panel factorisation per SM (tuning knob BK_QR_PER_SM, with BK_QR_ROWS = rows per CTA)
+static int qr_ctas_per_sm() {
+  static const int v = getenv("BK_QR_PER_SM") ? std::max(1, std::min(2, atoi(getenv("BK_QR_PER_SM")))) : 1;
+  return v;
+}
 
 struct PanelArgs {
   double* A;        // n x n, lda
@@ -250,7 +255,7 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
   const int G = ctx->sm_count;
   DevBuf<double> taus, part, prow, S, VT, S2, S3, PAbuf, PBbuf;
   BK_TRY(taus.alloc(b));
-  BK_TRY(part.alloc((size_t)2 * G * b));
+  BK_TRY(part.alloc((size_t)2 * G * qr_ctas_per_sm() * b));
   BK_TRY(prow.alloc(2 * b));
   BK_TRY(S.alloc(b * b));
   BK_TRY(VT.alloc((size_t)n * b));
@@ -260,7 +265,7 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
   BK_TRY(PBbuf.borrow(ctx->panel_cache[1], (size_t)4 * b * n));
   BK_TRY(ctx->barrier.ensure(4));
   static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
-  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), G));
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), (int64_t)G * qr_ctas_per_sm()));
   const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
   BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
   BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -295,7 +300,7 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
     pa.prow = prow.p;
     pa.barrier = ctx->barrier.p;
     pa.prof = nullptr;
-    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(G, ceil_div(m, rows_target)));
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)G * qr_ctas_per_sm(), ceil_div(m, rows_target)));
     pa.rows_per = (int)ceil_div(m, Gp);
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
     void* kargs[] = {&pa};
@@ -386,7 +391,7 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   const int G = ctx->sm_count;
   DevBuf<double> taus, part, prow, S, T, VT, S2, S3;
   BK_TRY(taus.alloc(b));
-  BK_TRY(part.alloc((size_t)2 * G * b));
+  BK_TRY(part.alloc((size_t)2 * G * qr_ctas_per_sm() * b));
   BK_TRY(prow.alloc(2 * b));
   BK_TRY(S.alloc(b * b));
   BK_TRY(T.alloc(b * b));
@@ -397,7 +402,7 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   // Rows of the panel per CTA (lower bound; all SMs are used while m >= rows_target * SMs).  Measured: the
   // per-column cost is dominated by the per-CTA slab work, not by the grid barrier - thin slabs win.
   static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
-  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), G));
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), (int64_t)G * qr_ctas_per_sm()));
   const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
   BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
   BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -462,7 +467,7 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     pa.prow = prow.p;
     pa.barrier = ctx->barrier.p;
     pa.prof = prof.p;
-    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(G, ceil_div(m, rows_target)));
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)G * qr_ctas_per_sm(), ceil_div(m, rows_target)));
     pa.rows_per = (int)ceil_div(m, Gp);
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, ctx->stream));
     void* kargs[] = {&pa};
@@ -705,7 +710,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   BK_TRY(Aloc.borrow(aloc_cache, (size_t)n * std::max(1, ncl)));
   BK_TRY(Xg.alloc((size_t)std::max(1, ncl) * p));
   BK_TRY(taus.alloc(b));
-  BK_TRY(part.alloc((size_t)2 * ctx->sm_count * b));
+  BK_TRY(part.alloc((size_t)2 * ctx->sm_count * qr_ctas_per_sm() * b));
   BK_TRY(prow.alloc(2 * b));
   BK_TRY(S.alloc(b * b));
   BK_TRY(VT.alloc((size_t)n * b));
@@ -721,7 +726,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   const size_t blk = (size_t)b * n;
 
   static const int rows_target = getenv("BK_QR_ROWS") ? atoi(getenv("BK_QR_ROWS")) : 128;
-  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), ctx->sm_count));
+  const int max_rows_per = std::max(rows_target, (int)ceil_div(std::max(1, n - b), (int64_t)ctx->sm_count * qr_ctas_per_sm()));
   const size_t max_smem = (size_t)max_rows_per * (b + 1) * sizeof(double);
   BK_REQUIRE(max_smem <= 200 * 1024, "sy2sb: n too large for the shared-memory panel slabs");
   BK_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -770,7 +775,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     pa.prow = prow.p;
     pa.barrier = ctx->barrier.p;
     pa.prof = nullptr;
-    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, ceil_div(m, rows_target)));
+    const int Gp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * qr_ctas_per_sm(), ceil_div(m, rows_target)));
     pa.rows_per = (int)ceil_div(m, Gp);
     BK_CUDA(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned) * 4, cs));
     void* kargs[] = {&pa};
@@ -793,12 +798,18 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     return BK_OK;
   };
 
+  const bool prof = getenv("BK_DIST_PROF") != nullptr;
+  size_t n_pev = 2;
+  auto pmark = [&]() {
+    if (prof) cudaEventRecord(pool_event(ctx, n_pev++), main_st);
+  };
   int J = 0;
   bool factored_ahead = false;  // this rank owns the current panel and factored it on the side stream already
   for (; J < nbk; ++J) {
     const int c0 = J * b, r0 = c0 + b, m = n - r0;
     if (m < 2) break;
     const int owner = J % G, q = J & 1;
+    pmark();  // 0: panel start
     double* PA = PAbuf.p + (size_t)q * 2 * blk;  // [V | W]
     double* PB = PBbuf.p + (size_t)q * 2 * blk;  // [W | V]
     double* Tk = Tstore + (size_t)J * b * b;
@@ -816,7 +827,9 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
       BK_LAUNCHED(ctx);
       BK_CUDA(cudaMemcpyAsync(Tk, vrecv + panel_elems, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, st));
     }
+    pmark();  // 1: panel available (owner: factored / joined; others: received + unpacked)
     BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, PA + r0, n, Tk, b, 0.0, VT.p, m));  // V T
+    pmark();  // 2: V T
     // ---- own rows of Z = A22 (V T): the local active columns, transposed
     const int lb0 = (J >= g) ? (J - g) / G + 1 : 0;  // local blocks with global index <= J are done
     const int lc0 = lb0 * b;
@@ -827,6 +840,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
       flops += 2.0 * nact * (double)m * b;
       ++launches;
     }
+    pmark();  // 3: own rows of Z
     {
       const long long tot = (long long)std::max(1, nact) * b;
       dist_zpush_kernel<<<(unsigned)std::min<long long>(ceil_div(tot, 512), 2LL * ctx->sm_count), 256, 0, st>>>(
@@ -834,6 +848,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
       BK_LAUNCHED(ctx);
     }
     BK_TRY(peer_wait(peer, CH_ZGATHER, all, seqZ, st));
+    pmark();  // 4: Z gathered
     // ---- W = Z - 1/2 V (T' (V'Z))  (replicated)
     const double* Zfull = peer_ptr(peer, z_off[q]);
     BK_TRY(copy_matrix(ctx, Zfull + r0, n, m, b, 1.0, PA + blk + r0, n));
@@ -841,6 +856,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));
     BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, PA + r0, n, S3.p, b, 1.0, PA + blk + r0, n));
     BK_TRY(copy_matrix(ctx, PA + blk + r0, n, m, b, 1.0, PB + r0, n));
+    pmark();  // 5: W
     // ---- A[:, own active columns] -= [V W] [W_g V_g]'
     if (nact > 0) {
       const long long tot = (long long)nact * 2 * b;
@@ -868,8 +884,10 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
       }
       flops += 2.0 * m * (double)nact * 2 * b;
     }
+    pmark();  // 6: update queued behind
   }
   if (factored_ahead) BK_CUDA(cudaStreamWaitEvent(main_st, e_fact, 0));
+  const int n_panels = J;
   double* PA = PAbuf.p;
   double* PB = PBbuf.p;
   // ---- the remaining (unfactored) diagonal blocks reach everyone the same way
@@ -898,6 +916,24 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
   // nobody re-uses (resets) the symmetric buffers before every rank is through
   BK_TRY(peer_barrier(peer, st));
   BK_TRY(peer_check(peer, st));
+  if (prof && n_panels > 0) {
+    // mean seconds per segment on this rank, panels it owns vs panels it receives
+    const char* seg[6] = {"panel ready", "V T", "Z rows (GEMM)", "Z gather", "W", "update"};
+    double own[6] = {0}, oth[6] = {0};
+    int n_own = 0, n_oth = 0;
+    for (int Jp = 0; Jp < n_panels; ++Jp) {
+      const bool mine = (Jp % G) == g;
+      (mine ? n_own : n_oth)++;
+      for (int i = 0; i < 6; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->event_pool[2 + 7 * Jp + i], ctx->event_pool[2 + 7 * Jp + i + 1]);
+        (mine ? own : oth)[i] += ms * 1e-3;
+      }
+    }
+    fprintf(stderr, "[sy2sb_dist prof rank %d/%d, n=%d] total seconds by segment (owned %d panels | received %d panels):\n", g, G, n,
+            n_own, n_oth);
+    for (int i = 0; i < 6; ++i) fprintf(stderr, "    %-16s %.4f | %.4f\n", seg[i], own[i], oth[i]);
+  }
   if (stats) {
     // per-rank flops of the Z products and updates; the launches are not bracketed by events in this variant
     stats->gemm_launches = launches;
