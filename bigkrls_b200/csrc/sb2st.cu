@@ -48,7 +48,66 @@ struct ChaseArgs {
   double* d;
   double* e;
   long long* prof;  // optional (BK_CHASE_PROF): [0] hops, [1] wait, [2] group A busy, [3] group B busy, [4] hop total
+  long long* trace;        // optional (BK_CHASE_TRACE=j0): SM clock at 12 points of hops 0..TR_HOPS-1 of sweeps j0..j0+TR_SWEEPS-1
+  int trace_j0;
+  unsigned long long* ll;  // early hand-off slots: LL_RING x maxhops x LL_PER_HOP x 2 tagged words (LLP kernel)
+  int* err;                // set when a hand-off wait gives up (cannot happen with all CTAs co-resident)
 };
+
+// ---- early hand-off between neighbouring sweeps ("late column") -----------------------------------------------
+// Hop (j, t) reads what sweep j-1 left behind.  All of it is final once sweep j-1 has finished hop t, EXCEPT the
+// last column of the block below the diagonal block and the two corners: those 65 numbers are the first column of
+// the diagonal block of hop (j-1, t+1) and the head of its new bulge column - known to sweep j-1 about 40 % into
+// that hop.  Waiting for the completion flag of (j-1, t+1) (store fence, flag flight, poll, then 64 KB of loads)
+// made the lag between neighbouring sweeps two full hops plus ~4500 cycles of flag latency; the lag is what bounds
+// the kernel (n sweeps, one after the other).  The LLP kernel therefore
+//   * hands the 65 late numbers over through self-validating slots (each 8-byte word = 32 bits of payload + a
+//     32-bit tag naming the producing sweep, as in NCCL's LL protocol: no fence, no separate flag), written as
+//     soon as they exist and polled by exactly the threads that need them; the producer does not store them into
+//     the band at all (the consumer owns those positions from then on), so the early start creates no race;
+//   * gives every CTA a ninth warp that does nothing but move data (chase_ws_kernel): it watches the completion flag
+//     of sweep j-1, stages everything else of the NEXT hop in shared memory with 16-byte cp.async while the eight
+//     compute warps work on the current one, and publishes this sweep's completion flags - the store fence of a
+//     release (1200-2500 cycles: it drains the whole SM's outstanding stores) and the 50 KB fetch of a hop
+//     (~2000 cycles) no longer sit on any compute thread's path.
+static constexpr int LL_RING = 4;           // sweeps whose slots are live at once (>= 2 by the dependency order)
+static constexpr int LL_PER_HOP = CB + 1;   // rows 0..63 of the column, then the corner of the block below
+static constexpr int TR_SWEEPS = 4, TR_HOPS = 48, TR_EV = 12;
+static constexpr int kSpinLimit = 1 << 22;  // polls before a wait gives up (seconds)
+static constexpr int SBN = CB + 2, SDN = CB + 1;  // column strides of the staging buffers (see chase_kernel)
+
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double val, unsigned tag) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(val);
+  const unsigned long long hi = (unsigned long long)tag << 32;
+  const unsigned long long w0 = hi | (u & 0xffffffffull), w1 = hi | (u >> 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};\n" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_try(const unsigned long long* slot, unsigned tag, double& val) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  val = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  return (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag;
+}
+__device__ __forceinline__ bool spin_giveup(int& spins, int* err) {
+  if (((++spins) & 1023) != 0) return false;
+  if (spins > kSpinLimit || *(volatile int*)err != 0) {
+    *(volatile int*)err = 1;
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ double ll_wait(const unsigned long long* slot, unsigned tag, int* err) {
+  double v;
+  int spins = 0;
+  while (!ll_try(slot, tag, v))
+    if (spin_giveup(spins, err)) break;
+  return v;
+}
+__device__ __forceinline__ void wait_prog(const int* p, int target, int* err) {
+  int spins = 0;
+  while (ld_acquire_i32(p) < target)
+    if (spin_giveup(spins, err)) break;
+}
 
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory"); }
 
@@ -113,10 +172,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
       long long tpa[6] = {0, 0, 0, 0, 0, 0};
       if (a.prof) tp0 = clock64();
       // ---- wait until sweep j-1 is two hops ahead (also orders the v <- v2 copy of the previous hop) -------
-      if (j > 0 && tid == 0) {
-        while (ld_acquire_i32(a.prog + j - 1) < t + 2) {
-        }
-      }
+      if (j > 0 && tid == 0) wait_prog(a.prog + j - 1, t + 2, a.err);
       __syncthreads();
       if (a.prof) tp1 = clock64();
       const bool has_b = hi < n;
@@ -328,6 +384,496 @@ __global__ void __launch_bounds__(CH_NT, 1) chase_kernel(ChaseArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised bulge chasing: 8 compute warps (the two groups of chase_kernel, same arithmetic in the same
+// order - d, e and the reflectors are bit-identical) + 1 transfer warp.
+//   transfer warp, per hop:  [flag of sweep j-1] -> stage the next hop's blocks (cp.async, completion on the mbarrier
+//                            s_full) ; [named barrier: this hop's stores are issued] -> release this sweep's flag
+//   compute warps, per hop:  wait s_full -> blocks from the staging buffers into registers -> arrive on s_empty
+//                            -> late numbers from the hand-off slots -> hop -> stores -> arrive on the named barrier
+// ---------------------------------------------------------------------------------------------------------
+// 8 compute warps + a warp group of 4 transfer warps (registers are handed out per warp group; setmaxnreg moves most
+// of the transfer group's share to the compute warps: 232 against 168 registers)
+static constexpr int WS_NT = CH_NT + 128;
+
+__device__ __forceinline__ void cta_sync256() { asm volatile("bar.sync 0, 256;\n" ::: "memory"); }
+// non-blocking phase test (try_wait may sleep in hardware; the transfer warp polls several things in turn)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded like every other wait of this kernel (try_wait sleeps in hardware for a while before it returns false)
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, unsigned parity, int* err) {
+  int spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1 << 16)) {
+      if (spins > (1 << 20) || *(volatile int*)err != 0) {
+        *(volatile int*)err = 1;
+        break;
+      }
+    }
+  }
+}
+// the mbarrier gets one arrival from this thread once all of its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Transfer warps (tw = warp 0..3, cl = lane): stage the blocks of the hop at `lo` (diagonal block L x L, block below
+// L2v x L; L2v = 0: none).
+//   block below: element (r, c) lives at pdn[L + r + 127 c]; pair k of column c = rows 2k - s, 2k - s + 1 with
+//   s = (L + c) & 1 (16-byte aligned in the band) -> Bn[66 c + 2 k]; rows >= L2v and columns >= L are zero-filled.
+//   diagonal block: column col, rows col + 2k, col + 2k + 1 at pdn[128 col + 2k] -> Dn[66 col + 2k].
+static constexpr int WS_SW = 4;  // staging warps
+__device__ __forceinline__ void ws_stage_hop(const double* __restrict__ AB, int lo, int L, int L2v, double* Bn,
+                                             double* Dn, int tw, int cl) {
+  const double* const pdn = AB + (size_t)lo * LDAB;
+  if (L == CB && L2v == CB) {
+    // full blocks: no predicates (the pair of rows 63, 64 of the early-starting columns brings one padding row)
+#pragma unroll
+    for (int m = 0; m < (CB + WS_SW - 1) / WS_SW; ++m) {
+      const int c = tw + WS_SW * m;
+      if (c < CB) cp_async16(Bn + c * SBN + 2 * cl, pdn + CB + c * (LDAB - 1) - (c & 1) + 2 * cl, 16);
+    }
+    if (tw == 0) {
+      const int c = 2 * cl + 1;
+      cp_async16(Bn + c * SBN + CB, pdn + CB + c * (LDAB - 1) - 1 + CB, 16);
+    }
+#pragma unroll
+    for (int m = 0; m < (CB / 2 + WS_SW - 1) / WS_SW; ++m) {
+      const int p = tw + WS_SW * m;
+      if (p < CB / 2) {
+        const int kp = (CB - p + 1) >> 1;  // pairs of column p; column 63-p has 33 - kp
+        const int col = (cl < kp) ? p : CB - 1 - p, k = (cl < kp) ? cl : cl - kp;
+        cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
+      }
+    }
+    if (tw == 1) {  // the 33rd pair of each column pair (p, 63-p): the last pair of column 63-p
+      const int p = cl, kp = (CB - p + 1) >> 1;
+      const int col = CB - 1 - p, k = 32 - kp;
+      cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
+    }
+    return;
+  }
+  if (L2v > 0) {
+#pragma unroll 4
+    for (int m = 0; m < (CB + WS_SW - 1) / WS_SW; ++m) {
+      const int c = tw + WS_SW * m;
+      if (c >= CB) break;
+      const int s = (L + c) & 1;
+      const int r0 = 2 * cl - s;
+      int nb = 0;
+      if (c < L) nb = (r0 + 1 < L2v) ? 16 : (r0 < L2v ? 8 : 0);
+      cp_async16(Bn + c * SBN + 2 * cl, nb ? pdn + L + c * (LDAB - 1) + r0 : AB, nb);
+    }
+    if (tw == 0) {
+      // the 33rd pair (rows 63, 64) of the columns that start one element early
+      const int c = 2 * cl + ((L + 1) & 1);
+      const int nb = (c < L && CB - 1 < L2v) ? 8 : 0;
+      cp_async16(Bn + c * SBN + CB, nb ? pdn + L + c * (LDAB - 1) + (CB - 1) : AB, nb);
+    }
+  }
+#pragma unroll 4
+  for (int m = 0; m < (CB / 2 + WS_SW - 1) / WS_SW; ++m) {
+    const int p = tw + WS_SW * m;
+    if (p >= CB / 2) break;
+    const int kp = (CB - p + 1) >> 1;
+    const int col = (cl < kp) ? p : CB - 1 - p, k = (cl < kp) ? cl : cl - kp;
+    const int row0 = col + 2 * k;
+    int nb = 0;
+    if (col < L) nb = (row0 + 1 < L) ? 16 : (row0 < L ? 8 : 0);
+    cp_async16(Dn + col * (SDN + 1) + 2 * k, nb ? pdn + (size_t)col * LDAB + 2 * k : AB, nb);
+  }
+  if (tw == 1) {
+    const int p = cl, kp = (CB - p + 1) >> 1;
+    const int col = CB - 1 - p, k = 32 - kp;
+    const int row0 = col + 2 * k;
+    int nb = 0;
+    if (col < L) nb = (row0 + 1 < L) ? 16 : (row0 < L ? 8 : 0);
+    cp_async16(Dn + col * (SDN + 1) + 2 * k, nb ? pdn + (size_t)col * LDAB + 2 * k : AB, nb);
+  }
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
+  extern __shared__ __align__(16) double chase_sm[];
+  double (*Ds)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chase_sm);
+  double (*Bs)[CB + 1] = Ds + CB;
+  // staging of the next hop's blocks: column strides 66 / 65 and the one-element shift of the columns that start
+  // 8 bytes off make every pair of rows a 16-byte aligned copy on both sides
+  double* const Bn = chase_sm + 2 * CB * (CB + 1);  // block below: (r, c) at [c * SBN + r + ((L + c) & 1)]
+  double* const Dn = Bn + CB * SBN;                 // diagonal block, lower triangle: (row, col) at [row + col * SDN]
+  double* const colv_s = Dn + CB * SDN;             // hop 0: column j below the diagonal (CB + 2 doubles)
+  __shared__ double v[CB], v2[CB], w[CB], w2[CB], wa[CB];
+  __shared__ double pA[2][CB], pD[2][CB], redA[4], redB[4];
+  __shared__ double s_alpha, s_tau0, s_tau2;
+  __shared__ __align__(8) uint64_t s_full, s_empty, s_done;
+  __shared__ int s_cmd[2];
+  const int n = a.n;
+  double* AB = a.AB;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_full, 32 * WS_SW);  // one deferred arrival per staging thread
+    mbar_init(&s_empty, CH_NT);   // every compute thread, once its staged numbers are in registers
+    mbar_init(&s_done, CH_NT);    // every compute thread, once its stores of the hop are issued
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= CH_NT) {
+    // =============================== transfer warps =====================================================
+    // Thread 0 of the group watches three things in turn - the completion flag of sweep j-1, the staging buffers
+    // (s_empty), this hop's stores (s_done) - and hands the group one command per round through shared memory.
+    // (Measured alternatives: one transfer warp - its 100 copies per hop take 8000 cycles to issue, a warp has only
+    // a few cp.async in flight; three staging warps + one publishing warp - 1750..5000 cycles per staging.)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    const int tt = tid - CH_NT, tw = tt >> 5, cl = tt & 31;
+    unsigned h = 0;       // hops of this CTA so far: parity of s_done
+    unsigned staged = 0;  // stagings issued so far: parity of s_full / s_empty
+    unsigned round = 0;
+    // hop (j, t) reads what sweep j-1 had finished after ITS hop t (the late numbers travel by the slots)
+    auto stage_ready = [&](int j, int t) -> bool {
+      if (j > 0 && ld_acquire_i32(a.prog + j - 1) < t + 1) return false;
+      if (staged > 0 && !mbar_test(&s_empty, (staged - 1) & 1u)) return false;  // previous staging still in use
+      return true;
+    };
+    auto stage = [&](int j, int t, int lo, int L, int L2v) {
+      ws_stage_hop(AB, lo, L, L2v, Bn, Dn, tw, cl);
+      if (t == 0 && tt < CB) {
+        const bool ok = tt < L;
+        cp_async8(colv_s + tt, ok ? AB + (1 + tt) + (size_t)j * LDAB : AB, ok ? 8 : 0);
+      }
+      cp_async_arrive_noinc(&s_full);
+      ++staged;
+    };
+    for (int j = blockIdx.x; j < n - 2; j += gridDim.x) {
+      bool any = false;
+      for (int t = 0;; ++t) {
+        const int lo = j + 1 + t * CB;
+        if (lo >= n) break;
+        const int hi = min(n, lo + CB), L = hi - lo;
+        if (t == 0 && L < 2) break;
+        const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
+        const bool has_b = hi < n;
+        const bool more = has_b && (L2 >= 2);
+        any = true;
+        long long* const trp = (TRACE && j >= a.trace_j0 && j < a.trace_j0 + TR_SWEEPS && t < TR_HOPS)
+                                   ? a.trace + ((size_t)(j - a.trace_j0) * TR_HOPS + t) * TR_EV
+                                   : nullptr;
+        int spins = 0;
+        // commands: 1 publish this hop (its stores are issued), 2 stage hop 0, 3 stage the next hop, 4 give up
+        bool need_first = (t == 0), need_stage = more, need_rel = true;
+        while (need_first || need_stage || need_rel) {
+          if (tt == 0) {
+            int cmd = 0;
+            if (need_first) {
+              if (stage_ready(j, 0)) cmd = 2;
+            } else if (need_rel && mbar_test(&s_done, h & 1u)) {
+              cmd = 1;
+            } else if (need_stage && stage_ready(j, t + 1)) {
+              cmd = 3;
+            }
+            if (cmd == 0 && spin_giveup(spins, a.err)) cmd = 4;
+            s_cmd[round & 1u] = cmd;
+          }
+          asm volatile("bar.sync 3, 128;\n" ::: "memory");
+          const int cmd = s_cmd[round & 1u];
+          ++round;
+          if (cmd == 1) {
+            if (tt == 0) {
+              st_release_i32(a.prog + j, more ? t + 1 : INT_MAX);
+              if (TRACE && trp) trp[11] = clock64();
+            }
+            need_rel = false;
+          } else if (cmd == 2) {
+            stage(j, 0, lo, L, has_b ? L2 : 0);
+            need_first = false;
+          } else if (cmd == 3) {
+            if (TRACE && trp && tt == 0) trp[8] = clock64();
+            const int hi3 = min(n, hi2 + CB);
+            stage(j, t + 1, hi, L2, (hi2 < n) ? hi3 - hi2 : 0);
+            if (TRACE && trp && tt == 0) trp[9] = clock64();
+            need_stage = false;
+          } else if (cmd == 4) {
+            need_first = need_stage = need_rel = false;
+          }
+        }
+        ++h;
+        if (!more) break;
+      }
+      if (!any && tt == 0) st_release_i32(a.prog + j, INT_MAX);
+    }
+    return;
+  }
+
+  // ================================= compute warps ========================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+  const int grp = tid >> 7, gt = tid & 127, gw = gt >> 5, lane = tid & 31;
+  const int r = gt & (CB - 1), cq = gt >> 6;
+  unsigned h = 0;
+  for (int j = blockIdx.x; j < n - 2; j += gridDim.x) {
+    double tau = 0.0;
+    for (int t = 0;; ++t) {
+      const int lo = j + 1 + t * CB;
+      if (lo >= n) break;
+      const int hi = min(n, lo + CB), L = hi - lo;
+      if (t == 0 && L < 2) break;
+      const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
+      const bool has_b = hi < n;
+      const bool more = has_b && (L2 >= 2);
+      const int Lrt = L, L2rt = L2;
+      long long* const trp = (TRACE && j >= a.trace_j0 && j < a.trace_j0 + TR_SWEEPS && t < TR_HOPS)
+                                 ? a.trace + ((size_t)(j - a.trace_j0) * TR_HOPS + t) * TR_EV
+                                 : nullptr;
+#define CH_TRACE(ev, who) \
+  if (TRACE && trp && tid == (who)) trp[ev] = clock64();
+      CH_TRACE(0, 0)
+      // Late numbers: hop (j-1, t+1) exists exactly when this hop has a block below its diagonal block; it hands
+      // over the first column of its diagonal block (the corner D[63][63] and B[0 .. L2-1][63], except B[63][63]) and,
+      // when it has a block below itself (L2 = 64), the head of its bulge column (B[63][63]).  Conversely every hop
+      // t >= 1 is such a hop for the next sweep: it hands those numbers over and does not store them.
+      const bool late = j > 0 && has_b;
+      const bool emit = t >= 1;
+      const unsigned long long* const ll_in =
+          a.ll + ((size_t)((j + LL_RING - 1) % LL_RING) * a.maxhops + (t + 1)) * (2 * LL_PER_HOP);
+      unsigned long long* const ll_out = a.ll + ((size_t)(j % LL_RING) * a.maxhops + t) * (2 * LL_PER_HOP);
+      const unsigned tag_in = (unsigned)j, tag_out = (unsigned)j + 1u;
+      // ---- the staged blocks of this hop have landed (also orders the v <- v2 copy of the previous hop) ------
+      mbar_wait_b(&s_full, h & 1u, a.err);
+      cta_sync256();
+      CH_TRACE(1, 0)
+      auto hop = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int L = FULL ? CB : Lrt, L2 = FULL ? CB : L2rt;
+        double* const pb = AB + (size_t)lo * LDAB + (L + r);  // block below the diagonal block, row hi + r
+        double* const pd0 = AB + (size_t)lo * LDAB;           // diagonal block: (row, col) at pd0[row + col (LDAB-1)]
+        double x[32];
+        double colv = 0.0;
+        if (grp == 0) {
+          if (has_b) {
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              x[i] = Bn[c * SBN + r + ((L + c) & 1)];  // zero outside the block
+            }
+          }
+          if (t == 0 && gt < L) colv = colv_s[gt];
+        } else {
+  #pragma unroll
+          for (int q = 0; q < 17; ++q) {
+            int row, col;
+            const bool ok = tri_slot(q, gw, lane, row, col) && (FULL || row < L);
+            x[q] = ok ? Dn[row + col * SDN] : 0.0;
+          }
+        }
+        mbar_arrive(&s_empty);  // this thread's staged numbers are in registers
+        if (t == 0) {
+          // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
+          if (grp == 0) {
+            double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redA[gw] = s;
+            if (gt == 0) s_alpha = colv;
+            group_bar(1);
+            double beta, tau0, scale;
+            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
+            if (gt < L) v[gt] = (gt == 0) ? 1.0 : colv * scale;
+            if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
+            if (gt == 0) {
+              AB[1 + (size_t)j * LDAB] = beta;
+              a.e[j] = beta;
+              a.d[j] = __ldcg(AB + (size_t)j * LDAB);
+              s_tau0 = tau0;
+            }
+          }
+          cta_sync256();
+          tau = s_tau0;
+        }
+        if (grp == 1) {
+          // ================= group B: two-sided update of D = A[lo:hi, lo:hi] =================================
+          if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
+          if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
+  #pragma unroll
+          for (int q = 0; q < 17; ++q) {
+            int row, col;
+            if (tri_slot(q, gw, lane, row, col) && (FULL || row < L)) {
+              Ds[row][col] = x[q];
+              Ds[col][row] = x[q];
+            }
+          }
+          group_bar(2);
+          {
+            // w = tau D v: half of the columns per thread, row r
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
+            if (r < L) {
+              const int c0 = cq * 32;
+  #pragma unroll
+              for (int c = 0; c < 31; ++c)
+                if (c0 + c < L) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
+              // late: the corner D[63][63] is the last term of row 63, so everything above runs before the hand-off
+              // has to be there
+              double dl = Ds[r][c0 + 31];
+              if (late && gt == 2 * CB - 1) {
+                dl = ll_wait(ll_in, tag_in, a.err);
+                Ds[CB - 1][CB - 1] = dl;
+              }
+              if (c0 + 31 < L) sa[3] = fma(dl, v[c0 + 31], sa[3]);
+            }
+            pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+          }
+          CH_TRACE(5, 255)
+          group_bar(2);
+          if (late && gt == 0) x[16] = Ds[CB - 1][CB - 1];  // slot 16 of thread 0 is that corner
+          {
+            const double wr0 = (gt < L) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
+            if (gt < CB) w[gt] = wr0;
+            double s = (gt < L) ? wr0 * v[gt] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redB[gw] = s;
+          }
+          group_bar(2);
+          {
+            const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
+            if (gt < CB) w2[gt] = (gt < L) ? fma(al, v[gt], w[gt]) : 0.0;  // w + al v
+            group_bar(2);
+  #pragma unroll
+            for (int q = 0; q < 17; ++q) {
+              int row, col;
+              if (tri_slot(q, gw, lane, row, col) && (FULL || row < L)) {
+                const double val = x[q] - v[row] * w2[col] - w2[row] * v[col];
+                if (q < 2 && emit && col == 0)
+                  ll_store(ll_out + 2 * row, val, tag_out);  // first column: handed to sweep j+1, not stored
+                else
+                  pd0[row + col * (LDAB - 1)] = val;
+              }
+            }
+          }
+          CH_TRACE(6, 128)
+        } else if (has_b) {
+          // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
+          {
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
+  #pragma unroll
+            for (int i = 0; i < 31; ++i) {
+              const int c = cq + 2 * i;
+              if (c < L) sa[i & 3] = fma(x[i], v[c], sa[i & 3]);
+            }
+            // late: column 63 of the block = first column of the diagonal block of hop (j-1, t+1), rows 1..63, and the
+            // head of that hop's bulge column; it enters the sums last, so the wait sits as deep in the hop as it can
+            if (late && cq == 1 && (r < CB - 1 ? r < L2 : L2 == CB))
+              x[31] = ll_wait(ll_in + 2 * (r < CB - 1 ? r + 1 : CB), tag_in, a.err);
+            CH_TRACE(2, 64)
+            if (cq + 62 < L) sa[3] = fma(x[31], v[cq + 62], sa[3]);
+            pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+          }
+          group_bar(1);
+          {
+            const double ur = tau * (pA[0][r] + pA[1][r]);
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              if (c < L) x[i] = fma(-ur, v[c], x[i]);
+            }
+          }
+          if (more) {
+            // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
+            double s = (cq == 0 && r >= 1 && r < L2) ? x[0] * x[0] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) redA[gw] = s;
+            if (gt == 0) s_alpha = x[0];
+            group_bar(1);
+            double beta, tau2, scale;
+            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
+            if (cq == 0) {
+              if (r < L2) v2[r] = (r == 0) ? 1.0 : x[0] * scale;
+              x[0] = (r == 0) ? beta : 0.0;
+            }
+            if (gt == 0) s_tau2 = tau2;
+            if (emit && gt == 0) ll_store(ll_out + 2 * CB, beta, tag_out);  // head of the new bulge column
+            CH_TRACE(3, 0)
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cq + 2 * i;
+              if (r < L2 && c < L) Bs[r][c] = x[i];
+            }
+            group_bar(1);
+            {
+              // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
+              double sa[4] = {0.0, 0.0, 0.0, 0.0};
+              if (r < L) {
+                const int q0 = cq * 32;
+  #pragma unroll
+                for (int q = 0; q < 32; ++q)
+                  if (q0 + q < L2) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
+              }
+              pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+            }
+            group_bar(1);
+            if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
+            group_bar(1);
+            {
+              const double v2r = (r < L2) ? v2[r] : 0.0;
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = cq + 2 * i;
+                if (c >= 1 && c < L) x[i] = fma(-v2r, wa[c], x[i]);
+              }
+            }
+          } else if (emit && gt == 0) {
+            ll_store(ll_out + 2 * CB, x[0], tag_out);  // no further reflector: the element as the right-update left it
+          }
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            const int dd = L + r - c;
+            if (i == 0 && emit && gt == 0) continue;  // handed over above
+            if (FULL || (r < L2 && c < L && dd < LDAB)) pb[c * (LDAB - 1)] = x[i];
+          }
+          CH_TRACE(4, 0)
+        }
+      };
+      if (L == CB && has_b && L2 == CB)
+        hop(std::true_type{});
+      else
+        hop(std::false_type{});
+      // this thread's stores of the hop are issued: the transfer warp publishes the hop once everybody is here
+      mbar_arrive(&s_done);
+      ++h;
+      cta_sync256();
+      CH_TRACE(10, 0)
+      if (more) {
+        if (tid < L2) v[tid] = v2[tid];
+        tau = s_tau2;
+      }
+      if (!more) break;
+    }
+    cta_sync256();
+  }
+#undef CH_TRACE
+}
+
 // d[n-2], d[n-1], e[n-2] are never touched by a sweep with a reflector: read them off the band at the end
 __global__ void chase_tail_kernel(const double* __restrict__ AB, int n, double* d, double* e) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -339,9 +885,11 @@ __global__ void chase_tail_kernel(const double* __restrict__ AB, int n, double* 
 }
 
 int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops) {
-  DevBuf<int> prog;
+  DevBuf<int> prog, err;
   BK_TRY(prog.alloc(n));
+  BK_TRY(err.alloc(1));
   BK_CUDA(cudaMemsetAsync(prog.p, 0, sizeof(int) * n, ctx->stream));
+  BK_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
   ChaseArgs a;
   a.AB = AB;
   a.n = n;
@@ -351,25 +899,77 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   a.prog = prog.p;
   a.d = d;
   a.e = e;
-  DevBuf<long long> prof;
+  a.err = err.p;
+  a.ll = nullptr;
+  a.trace = nullptr;
+  a.trace_j0 = 0;
+  DevBuf<long long> prof, trace;
   a.prof = nullptr;
-  if (getenv("BK_CHASE_PROF")) {
+  // warp-specialised kernel with the early hand-off (default); BK_CHASE_LL=0 selects the completion-flag kernel
+  // (same bits; read per call: the tests compare both in one process)
+  const char* ll_env = getenv("BK_CHASE_LL");
+  const bool use_ws = !(ll_env && atoi(ll_env) == 0);
+  if (!use_ws && getenv("BK_CHASE_PROF")) {
     BK_TRY(prof.alloc(16));
     BK_CUDA(cudaMemsetAsync(prof.p, 0, 16 * sizeof(long long), ctx->stream));
     a.prof = prof.p;
   }
+  const size_t trace_n = (size_t)TR_SWEEPS * TR_HOPS * TR_EV;
+  if (const char* tj = getenv("BK_CHASE_TRACE")) {
+    if (use_ws) {
+      BK_TRY(trace.alloc(trace_n));
+      BK_CUDA(cudaMemsetAsync(trace.p, 0, trace_n * sizeof(long long), ctx->stream));
+      a.trace = trace.p;
+      a.trace_j0 = atoi(tj);
+    }
+  }
+  DevBuf<unsigned long long> ll;
+  if (use_ws) {
+    const size_t words = (size_t)LL_RING * maxhops * LL_PER_HOP * 2;
+    BK_TRY(ll.alloc(words));
+    BK_CUDA(cudaMemsetAsync(ll.p, 0, sizeof(unsigned long long) * words, ctx->stream));  // tag 0 = never written
+    a.ll = ll.p;
+  }
   if (n > 2) {
     void* kargs[] = {&a};
-    const size_t smem = sizeof(double) * 2 * CB * (CB + 1);
-    BK_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BK_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctx->sm_count), dim3(CH_NT), kargs, smem,
-                                        ctx->stream));
+    if (use_ws) {
+      const size_t smem = sizeof(double) * (2 * CB * (CB + 1) + CB * (SBN + SDN) + CB + 2);
+      void* kern = a.trace ? (void*)chase_ws_kernel<true> : (void*)chase_ws_kernel<false>;
+      BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      BK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(ctx->sm_count), dim3(WS_NT), kargs, smem, ctx->stream));
+    } else {
+      const size_t smem = sizeof(double) * 2 * CB * (CB + 1);
+      BK_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      BK_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctx->sm_count), dim3(CH_NT), kargs, smem,
+                                          ctx->stream));
+    }
     BK_LAUNCHED(ctx);
   }
   chase_tail_kernel<<<1, 32, 0, ctx->stream>>>(AB, n, d, e);
   BK_LAUNCHED(ctx);
   BK_CUDA(cudaGetLastError());
+  int herr = 0;
+  BK_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (herr != 0) {
+    set_error("sb2st: a hand-off between sweeps of the bulge chasing never arrived");
+    return BK_ERR_NUMERIC;
+  }
+  if (a.trace) {
+    // one line per traced hop: sweep, hop, then the clock readings relative to the first hop of the sweep
+    std::vector<long long> h(trace_n);
+    BK_CUDA(cudaMemcpyAsync(h.data(), trace.p, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int sj = 0; sj < TR_SWEEPS; ++sj)
+      for (int th = 0; th < TR_HOPS; ++th) {
+        const long long* e0 = h.data() + ((size_t)sj * TR_HOPS) * TR_EV;
+        const long long* ev = h.data() + ((size_t)sj * TR_HOPS + th) * TR_EV;
+        if (ev[0] == 0) continue;
+        fprintf(stderr, "[chase trace] %d %d", a.trace_j0 + sj, th);
+        for (int q = 0; q < TR_EV; ++q) fprintf(stderr, " %lld", ev[q] ? ev[q] - e0[0] : -1LL);
+        fprintf(stderr, "\n");
+      }
+  }
   if (a.prof) {
     long long h[16];
     BK_CUDA(cudaMemcpyAsync(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

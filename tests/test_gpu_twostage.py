@@ -56,6 +56,28 @@ def test_twostage(ctx, n, p, k):
     assert orth < 1e-12 * np.sqrt(n), orth
 
 
+@pytest.mark.parametrize("n", [130, 193, 200, 257, 517, 1000, 3001, 6007])
+def test_chase_handoff_protocols_agree_bitwise(ctx, monkeypatch, n):
+    """The early hand-off kernel (tagged slots + staged blocks, sb2st.cu) runs the same arithmetic as the
+    completion-flag kernel: tridiagonal, band and back-transformed vectors must be bit-identical (sizes around the
+    first full hop, 1 + 3*64 rows, and several CTAs' worth of sweeps)."""
+    lib = _lib.load()
+    A = kernel_matrix(n, 4)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("BK_CHASE_LL", flag)
+        d = np.zeros(n)
+        e = np.zeros(n)
+        check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), None, 0, None))
+        k = min(n, 96)
+        Z = np.asfortranarray(np.random.default_rng(7).standard_normal((n, k)))
+        check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), dptr(Z), k, None))
+        out[flag] = (d.copy(), e.copy(), Z.copy())
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert np.array_equal(out["0"][2], out["1"][2])
+
+
 @pytest.mark.parametrize("n,p,k", [(66, 3, 66), (517, 6, 100), (1000, 4, 1000), (3001, 5, 400)])
 def test_q2_blocked_backtransform(ctx, monkeypatch, n, p, k):
     """The GEMM-based (compact-WY blocks) Q2 back-transformation, forced for every k (odd n: unaligned path)."""
