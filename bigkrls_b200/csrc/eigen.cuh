@@ -88,7 +88,7 @@ int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long 
 // Collective full eigensolver on the kernel matrix of X: stage 1 on all ranks, the rest on rank 0.  Only rank 0
 // fills evals_host / n_want / Z; the caller broadcasts.
 int eigen_full_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
-                    double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
+                    double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z, long long ldz, size_t off_Q,
                     EigenTimes* times);
 static constexpr int kTwoStageFullMax = 16384;  // largest n for which the two-stage path is taken for ALL vectors
 bool use_twostage(int n, int max_want, double rel_thresh);

@@ -445,9 +445,11 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
       f->info.krylov_restarts = ts.restarts;
       replicated = true;
     } else if (dist_eig) {
-      // dense -> band distributed over all ranks, band -> tridiagonal, D&C and back-transformation on rank 0
-      eig_rc = eigen_full_dist(ctx, peer, f->X.p, ld, p, o.sigma, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, &et);
-      if (eig_rc == BK_ERR_CUDA || eig_rc == BK_ERR_COMM) return eig_rc;
+      // dense -> band distributed over all ranks; band -> tridiagonal and D&C on every rank (same bits); the
+      // back-transformation split by columns and all-gathered - every rank returns with the complete result
+      BK_TRY(eigen_full_dist(ctx, peer, f->X.p, ld, p, o.sigma, n, ev.data(), f->neig, o.eigtrunc, &k, Zfull.p, ld, off_Q,
+                             &et));
+      replicated = true;
     } else if (!multi || rank == 0) {
       DevBuf<double> Kfull;
       const double* Kmat = f->K.p;

@@ -148,47 +148,91 @@ static int eigen_full_twostage(bk_ctx* ctx, const double* K, long long ldk, int 
   return BK_OK;
 }
 
+// Distributed variant.  Stage 1 (dense -> band) is spread over the ranks; every rank then holds the complete band and
+// runs the band -> tridiagonal stage and the divide & conquer itself (deterministic: the same bits everywhere, and
+// cheaper than waiting for rank 0 and a broadcast of the stage-2 reflectors); the back-transformation - the part
+// whose cost grows with the number of eigenvectors - is split by columns and the blocks are all-gathered through the
+// symmetric buffer at heap offset off_Q (n x max_want doubles, ld n = ldz).  Every rank returns the same status.
 int eigen_full_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
                     double* evals_host, int max_want, double rel_thresh, int* n_want, double* Z, long long ldz,
-                    EigenTimes* times) {
+                    size_t off_Q, EigenTimes* times) {
+  BK_REQUIRE(ldz == n, "eigen_full_dist: the eigenvector block must be dense (ld = n)");
   Timer tm;
   BK_TRY(tm.init(ctx->stream));
-  DevBuf<double> d, e;
+  DevBuf<double> d, e, agree;
   BK_TRY(d.alloc(n));
   BK_TRY(e.alloc(n));
+  BK_TRY(agree.alloc(2));
   BK_CUDA(cudaMemsetAsync(e.p, 0, sizeof(double) * n, ctx->stream));
   TwoStage ts;
   tm.start();
   BK_TRY(twostage_reduce_dist(ctx, peer, X, ldx, p, sigma, n, &ts, d.p, e.p));
   const double t_tri = tm.stop();
+  if (n_want) *n_want = 0;
+  std::vector<double> dh(n), eh(n), ev(n);
+  BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = BK_OK;
+  for (int i = 0; i < n && rc == BK_OK; ++i)
+    if (!std::isfinite(dh[i]) || !std::isfinite(eh[i])) {
+      set_error("eigen: tridiagonalisation produced a non-finite entry (NaN/Inf in the input?)");
+      rc = BK_ERR_NUMERIC;
+    }
+  tm.start();
+  int nw = 0;
+  StedcStats st;
+  if (rc == BK_OK) {
+    rc = stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st);
+    if (rc == BK_ERR_CUDA) return rc;
+  }
+  const double t_dc = tm.stop();
+  // agreement before anybody enters the all-gather: a numerical failure (or a different count of retained
+  // eigenvectors) on one rank must surface as the same error everywhere, not as a rank waiting in a collective
+  {
+    const double mine[2] = {rc != BK_OK ? 1.0 : 0.0, (double)nw};
+    double all[2];
+    BK_CUDA(cudaMemcpyAsync(agree.p, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    BK_TRY(peer_allreduce_sum(peer, agree.p, 2, ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(all, agree.p, sizeof(all), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (all[0] > 0.0) {
+      if (rc == BK_OK) set_error("the eigensolver failed on another rank");
+      return BK_ERR_NUMERIC;
+    }
+    if (all[1] != (double)nw * peer->world) {
+      set_error("eigen_full_dist: the ranks disagree on the number of retained eigenvectors");
+      return BK_ERR_NUMERIC;
+    }
+  }
+  tm.start();
+  if (Z && nw > 0) {
+    const int G = peer->world, g = peer->rank;
+    std::vector<long long> counts(G), displs(G);
+    for (int r = 0; r < G; ++r) {
+      const long long a = (long long)nw * r / G, b = (long long)nw * (r + 1) / G;
+      counts[r] = (b - a) * n;
+      displs[r] = a * n;
+    }
+    const int c0 = (int)((long long)nw * g / G), c1 = (int)((long long)nw * (g + 1) / G);
+    double* Qs = peer_ptr(peer, off_Q);
+    if (c1 > c0) {
+      BK_TRY(twostage_back(ctx, &ts, Z + (size_t)c0 * ldz, ldz, c1 - c0));
+      BK_CUDA(cudaMemcpyAsync(Qs + (size_t)c0 * n, Z + (size_t)c0 * ldz, sizeof(double) * (size_t)n * (c1 - c0),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    BK_TRY(peer_allgatherv_sym(peer, off_Q, counts.data(), displs.data(), ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(Z, Qs, sizeof(double) * (size_t)n * nw, cudaMemcpyDeviceToDevice, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  const double t_bt = tm.stop();
+  for (int i = 0; i < n; ++i) evals_host[i] = ev[n - 1 - i];
+  if (n_want) *n_want = nw;
   if (times) {
     times->tridiag = t_tri;
     times->twostage = 1;
     times->t_sy2sb = ts.t_sy2sb;
     times->band = ts.band;
-  }
-  if (n_want) *n_want = 0;
-  if (peer->rank != 0) return BK_OK;
-  std::vector<double> dh(n), eh(n), ev(n);
-  BK_CUDA(cudaMemcpyAsync(dh.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_CUDA(cudaMemcpyAsync(eh.data(), e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < n; ++i)
-    if (!std::isfinite(dh[i]) || !std::isfinite(eh[i])) {
-      set_error("eigen: tridiagonalisation produced a non-finite entry (NaN/Inf in the input?)");
-      return BK_ERR_NUMERIC;
-    }
-  tm.start();
-  int nw = 0;
-  StedcStats st;
-  BK_TRY(stedc(ctx, n, dh.data(), eh.data(), ev.data(), max_want, rel_thresh, &nw, Z, ldz, &st));
-  const double t_dc = tm.stop();
-  tm.start();
-  if (Z && nw > 0) BK_TRY(twostage_back(ctx, &ts, Z, ldz, nw));
-  const double t_bt = tm.stop();
-  for (int i = 0; i < n; ++i) evals_host[i] = ev[n - 1 - i];
-  if (n_want) *n_want = nw;
-  if (times) {
     times->dc = t_dc;
     times->backtransform = t_bt;
     times->dc_stats = st;

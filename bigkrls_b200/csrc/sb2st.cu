@@ -1366,7 +1366,7 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
 }
 
 // Multi-GPU variant: stage 1 distributed over the ranks of `peer` (sy2sb_dist, straight from X - the kernel matrix is
-// never gathered); every rank ends with the complete factored matrix, rank 0 runs the band -> tridiagonal stage.
+// never gathered); every rank ends with the complete factored matrix and runs the band -> tridiagonal stage itself.
 int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p, double sigma, int n,
                          TwoStage* ts, double* d, double* e) {
   const int b = CB;
@@ -1381,7 +1381,8 @@ int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long 
   tm.start();
   BK_TRY(sy2sb_dist(ctx, peer, X, ldx, p, sigma, n, ts->work.p, ts->Tstore.p, ts->AB.p, LDAB, ctx->ws[2], &ts->band));
   ts->t_sy2sb = tm.stop();
-  if (peer->rank != 0) return BK_OK;
+  // every rank holds the complete band: all of them chase it (same bits everywhere, nobody waits for a broadcast of
+  // the reflectors) so that each can back-transform its own share of the eigenvectors
   BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
   BK_CUDA(cudaMemsetAsync(ts->TAU.p, 0, sizeof(double) * (size_t)ts->maxhops * n, ctx->stream));
   BK_TRY(ts->VV.borrow(ctx->ws[1], (size_t)n * n));
