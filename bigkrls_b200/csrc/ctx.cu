@@ -244,6 +244,31 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
   if (s == 123.456) out[0] = s;
 }
 
+// both at once: 4 DMMA + 32 DFMA per warp and iteration (equal pipe time if the pipes are separate: 512 vs 64 flops
+// per warp instruction).  Tells whether the FP64 tensor path and the FP64 FMA path are the same hardware.
+__global__ void __launch_bounds__(256) dmma_dfma_mix_kernel(double* out, int iters) {
+  double c[4][2], a[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1.0 - 1e-9 * threadIdx.x, bb = 1.0000001, cc = 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dmma884(c[i][0], c[i][1], x, y);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[i * 8 + q] = fma(a[i * 8 + q], bb, cc);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
+
 __global__ void copy_peak_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                  long long n2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2;
@@ -410,6 +435,21 @@ int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result
       // DFMA: 2 flops per lane-op; DMMA m8n8k4: 8*8*4*2 flops per warp instruction
       const double flops = (kind == 0) ? (double)blocks * 256.0 * 16.0 * iters * 2.0
                                        : (double)blocks * 8.0 * 16.0 * iters * 512.0;
+      *result = flops / s * 1e-12;
+    }
+    return BK_OK;
+  }
+  if (kind == 6) {
+    BK_TRY(buf.alloc(16));
+    const int blocks = ctx->sm_count * 8;
+    if (iters <= 0) iters = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+      tm.start();
+      bk::dmma_dfma_mix_kernel<<<blocks, 256, 0, ctx->stream>>>(buf.p, iters);
+      BK_LAUNCHED(ctx);
+      const double s = tm.stop();
+      BK_CUDA(cudaGetLastError());
+      const double flops = (double)blocks * iters * (8.0 * 4.0 * 512.0 + 256.0 * 32.0 * 2.0);
       *result = flops / s * 1e-12;
     }
     return BK_OK;

@@ -229,6 +229,65 @@ __global__ void sb_larft_kernel(const double* __restrict__ S, const double* __re
   for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) T[idx] = ts[(idx % ib) * ib + idx / ib];
 }
 
+// The same T by inversion: for H = H_1 ... H_b = I - V T V' one has T^-1 = striu(V'V) + diag(1 / tau) exactly (for any
+// tau, orthogonal or not), so T is the inverse of an upper triangular matrix - built by doubling: with the inverses of
+// two neighbouring s x s diagonal blocks (A^-1, C^-1) and the block B above-right of them, the inverse of the 2s x 2s
+// block has -A^-1 B C^-1 there.  Six levels of small products with two barriers each instead of 64 dependent steps
+// (40 us -> ~8 us per panel, and T sits on the critical path of every panel).  A reflector with tau = 0 (H_i = I) is
+// decoupled (its row and column of T are zero).  One CTA of 256 threads, ib <= 64.
+__global__ void __launch_bounds__(256) sb_larft_inv_kernel(const double* __restrict__ S, const double* __restrict__ tau,
+                                                           int ib, double* __restrict__ T) {
+  extern __shared__ __align__(16) double li_sm[];
+  double (*U)[SB + 1] = reinterpret_cast<double (*)[SB + 1]>(li_sm);
+  double (*R)[SB + 1] = U + SB;
+  double (*Y)[SB + 1] = R + SB;
+  __shared__ double s_tau[SB];
+  const int tid = threadIdx.x;
+  if (tid < SB) s_tau[tid] = (tid < ib) ? tau[tid] : 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < SB * SB; idx += 256) {
+    const int i = idx % SB, j = idx / SB;
+    const bool live = s_tau[i] != 0.0 && s_tau[j] != 0.0;
+    double u = 0.0;
+    if (i == j)
+      u = (s_tau[i] != 0.0) ? 1.0 / s_tau[i] : 1.0;
+    else if (i < j && live)
+      u = S[i + j * ib];
+    U[i][j] = u;
+    R[i][j] = (i == j) ? ((s_tau[i] != 0.0) ? s_tau[i] : 1.0) : 0.0;
+  }
+  __syncthreads();
+  for (int sz = 1; sz < SB; sz *= 2) {
+    // element e of this level: pair p = e / (sz*sz), (i, j) inside the off-diagonal block
+    const int per = sz * sz, total = (SB / (2 * sz)) * per;
+    for (int e = tid; e < total; e += 256) {
+      const int pblk = e / per, i = (e % per) % sz, j = (e % per) / sz;
+      const int b0 = pblk * 2 * sz;
+      double acc = 0.0;  // Y = B C^-1 (C^-1 upper triangular: k <= j)
+      for (int k = 0; k <= j; ++k) acc = fma(U[b0 + i][b0 + sz + k], R[b0 + sz + k][b0 + sz + j], acc);
+      Y[b0 + i][b0 + sz + j] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += 256) {
+      const int pblk = e / per, i = (e % per) % sz, j = (e % per) / sz;
+      const int b0 = pblk * 2 * sz;
+      double acc = 0.0;  // X = -A^-1 Y (A^-1 upper triangular: k >= i)
+      for (int k = i; k < sz; ++k) acc = fma(R[b0 + i][b0 + k], Y[b0 + k][b0 + sz + j], acc);
+      R[b0 + i][b0 + sz + j] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < ib * ib; idx += 256) {
+    const int i = idx % ib, j = idx / ib;
+    double t = 0.0;
+    if (i == j)
+      t = s_tau[i];
+    else if (i < j && s_tau[i] != 0.0 && s_tau[j] != 0.0)
+      t = R[i][j];
+    T[idx] = t;
+  }
+}
+
 // AB[d + j*ldab] = A[j+d, j] for d <= b, 0 for b < d < ldab   (lower band, working width 2b)
 __global__ void extract_band_kernel(const double* __restrict__ A, long long lda, int n, int b,
                                     double* __restrict__ AB, int ldab) {
@@ -240,6 +299,33 @@ __global__ void extract_band_kernel(const double* __restrict__ A, long long lda,
     if (d <= b && j + d < n) v = A[(long long)(j + d) + (long long)j * lda];
     AB[idx] = v;
   }
+}
+
+// T from V'V and tau (one CTA): the doubling inverse by default, the 64-step recurrence with BK_LARFT_SEQ=1
+static void launch_larft(cudaStream_t st, const double* S, const double* tau, int ib, double* T) {
+  static const bool seq = getenv("BK_LARFT_SEQ") != nullptr;
+  if (seq)
+    sb_larft_kernel<<<1, 16 * ib, sizeof(double) * 2 * ib * ib, st>>>(S, tau, ib, T);
+  else {
+    constexpr size_t smem = sizeof(double) * 3 * SB * (SB + 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(sb_larft_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    sb_larft_inv_kernel<<<1, 256, smem, st>>>(S, tau, ib, T);
+  }
+}
+// W = Z - V (T' V'Z) / 2 in place of Z (Wd, rows r0..) and a copy into Wd2.  (One fused kernel for the last three
+// steps - every CTA forming T' V'Z itself, FMA loops - was measured slower than the three launches: +0.01 s per fit.)
+static int finish_w_fused(bk_ctx* ctx, int n, int r0, const double* Vd, double* Wd, double* Wd2, const double* Tk,
+                          double* S2, double* S3) {
+  const int b = SB, m = n - r0;
+  BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vd + r0, n, Wd + r0, n, 0.0, S2, b));   // V'Z
+  BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2, b, 0.0, S3, b));             // T' V'Z
+  BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, Vd + r0, n, S3, b, 1.0, Wd + r0, n)); // W = Z - V S3 / 2
+  BK_TRY(copy_matrix(ctx, Wd + r0, n, m, b, 1.0, Wd2 + r0, n));
+  return BK_OK;
 }
 
 // Look-ahead variant: one panel at a time, and the factorisation of panel k+1 (cooperative QR kernel, V'V, T, V T -
@@ -308,7 +394,7 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
     BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, ctx->stream));
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vd + r0, n, Vd + r0, n, 0.0, S.p, b));
-    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
+    launch_larft(ctx->stream, S.p, taus.p, b, Tk);
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vd + r0, n, Tk, b, 0.0, VT.p, m));
     return BK_OK;
@@ -331,10 +417,7 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
     mark();
     flops += 2.0 * m * (double)m * b;
     // W = Z - V (T' V'Z) / 2 in place, and the copy into [W | V]
-    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + blk + r0, n, 0.0, S2.p, b));
-    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));
-    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, PA + r0, n, S3.p, b, 1.0, PA + blk + r0, n));
-    BK_TRY(copy_matrix(ctx, PA + blk + r0, n, m, b, 1.0, PB + r0, n));
+    BK_TRY(finish_w_fused(ctx, n, r0, PA, PA + blk, PB, Tk, S2.p, S3.p));
     const int r1 = r0 + b, m2 = n - r1;
     if (m2 < 2) {
       // last panel: the whole trailing block (its lower triangle carries the final diagonal blocks of the band)
@@ -475,19 +558,14 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, ctx->stream));
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vd + r0, n, Vd + r0, n, 0.0, S.p, b));
-    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, ctx->stream>>>(S.p, taus.p, b, Tk);
+    launch_larft(ctx->stream, S.p, taus.p, b, Tk);
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, false, false, m, b, b, 1.0, Vd + r0, n, Tk, b, 0.0, VT.p, m));  // V T
     return BK_OK;
   };
   // W = Z - V (T' V'Z) / 2 in place of Z (Wd), and a copy into Wd2
   auto finish_w = [&](int r0, const double* Vd, double* Wd, double* Wd2, const double* Tk) -> int {
-    const int m = n - r0;
-    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, Vd + r0, n, Wd + r0, n, 0.0, S2.p, b));   // V'Z
-    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));           // T' V'Z
-    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, Vd + r0, n, S3.p, b, 1.0, Wd + r0, n)); // W = Z - V S3 / 2
-    BK_TRY(copy_matrix(ctx, Wd + r0, n, m, b, 1.0, Wd2 + r0, n));
-    return BK_OK;
+    return finish_w_fused(ctx, n, r0, Vd, Wd, Wd2, Tk, S2.p, S3.p);
   };
 
   int k = 0, pair = 0;
@@ -783,7 +861,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     BK_CUDA(cudaLaunchCooperativeKernel((void*)panel_qr_kernel, dim3(Gp), dim3(QR_NT), kargs, smem, cs));
     BK_LAUNCHED(ctx);
     BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PAq + r0, n, PAq + r0, n, 0.0, S.p, b));
-    sb_larft_kernel<<<1, 16 * b, sizeof(double) * 2 * b * b, cs>>>(S.p, taus.p, b, Tk);
+    launch_larft(cs, S.p, taus.p, b, Tk);
     BK_LAUNCHED(ctx);
     // T, then the factored panel (rows c0..n: diagonal block, R, V), into every other rank's HBM
     const double* pan = Aloc.p + c0 + (long long)lb * b * lda;
@@ -852,10 +930,7 @@ int sy2sb_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long ldx, int p
     // ---- W = Z - 1/2 V (T' (V'Z))  (replicated)
     const double* Zfull = peer_ptr(peer, z_off[q]);
     BK_TRY(copy_matrix(ctx, Zfull + r0, n, m, b, 1.0, PA + blk + r0, n));
-    BK_TRY(gemm(ctx, true, false, b, b, m, 1.0, PA + r0, n, PA + blk + r0, n, 0.0, S2.p, b));
-    BK_TRY(gemm(ctx, true, false, b, b, b, 1.0, Tk, b, S2.p, b, 0.0, S3.p, b));
-    BK_TRY(gemm(ctx, false, false, m, b, b, -0.5, PA + r0, n, S3.p, b, 1.0, PA + blk + r0, n));
-    BK_TRY(copy_matrix(ctx, PA + blk + r0, n, m, b, 1.0, PB + r0, n));
+    BK_TRY(finish_w_fused(ctx, n, r0, PA, PA + blk, PB, Tk, S2.p, S3.p));
     pmark();  // 5: W
     // ---- A[:, own active columns] -= [V W] [W_g V_g]'
     if (nact > 0) {
