@@ -513,7 +513,8 @@ def main():
     dmma = float(rr.value) * 1e12
     kk = float(info["lastkeeper"])
     # partitioned stages: the floor of ONE rank's share (work / world).  The eigensolver's floor is left at the
-    # single-GPU figure: only its dense->band stage is distributed, the rest runs on rank 0.
+    # single-GPU figure: only its dense->band stage and the back-transformation are distributed, the band->tridiagonal
+    # stage and the divide & conquer run on every rank (same bits, no broadcast).
     floors = {
         "t_kernel": 8.0 * N * N / world / (hbm_peak * 1e9),
         "t_eigen": ((4.0 / 3.0) * N ** 3 + 2.0 * N * N * kk) / dmma,
@@ -531,7 +532,8 @@ def main():
                        "seed": SEED, "l2": "inputs larger than L2 (K is %.1f GB)" % (8.0 * N * N * 1e-9),
                        "parallelism": (f"column blocks x{world}: kernel build, LOO, vcov, marginal effects partitioned; "
                                        f"dense->band stage of the eigensolver block-cyclic over the {world} GPUs "
-                                       f"(peer stores over NVLink), band->tridiagonal + D&C on rank 0") if world > 1
+                                       f"(peer stores over NVLink), band->tridiagonal + D&C replicated on every rank, "
+                                       f"back-transformation split by columns and all-gathered") if world > 1
                        else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(8 * N * (P + 1)),
