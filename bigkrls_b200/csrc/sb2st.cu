@@ -49,7 +49,8 @@ struct ChaseArgs {
   double* e;
   long long* prof;  // optional (BK_CHASE_PROF): [0] hops, [1] wait, [2] group A busy, [3] group B busy, [4] hop total
   long long* trace;        // optional (BK_CHASE_TRACE=j0): SM clock at 12 points of hops 0..TR_HOPS-1 of sweeps j0..j0+TR_SWEEPS-1
-  int trace_j0;
+  int trace_j0, trace_t0;
+  double* mb;              // mailboxes: 2 x maxhops x MB_STRIDE doubles (ws kernel)
   unsigned long long* ll;  // early hand-off slots: LL_RING x maxhops x LL_PER_HOP x 2 tagged words (LLP kernel)
   int* err;                // set when a hand-off wait gives up (cannot happen with all CTAs co-resident)
 };
@@ -73,8 +74,24 @@ struct ChaseArgs {
 static constexpr int LL_RING = 4;           // sweeps whose slots are live at once (>= 2 by the dependency order)
 static constexpr int LL_PER_HOP = CB + 1;   // rows 0..63 of the column, then the corner of the block below
 static constexpr int TR_SWEEPS = 4, TR_HOPS = 48, TR_EV = 12;
+__device__ __forceinline__ long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return (long long)t;
+}
+// global-timer stamps (kind 0: hop starts, 1: stores issued, 2: flag released, 3: staging of the hop commanded)
+#define CH_GSTAMP(kind, jj, tt_)                                                                         \
+  if (TRACE && (jj) >= a.trace_j0 && (jj) < a.trace_j0 + 16 && (tt_) >= a.trace_t0 && (tt_) < a.trace_t0 + 64)       \
+    a.trace[(size_t)TR_SWEEPS * TR_HOPS * TR_EV + ((size_t)(kind) * 16 + ((jj) - a.trace_j0)) * 64 + (tt_) - a.trace_t0] = global_ns();
 static constexpr int kSpinLimit = 1 << 22;  // polls before a wait gives up (seconds)
 static constexpr int SBN = CB + 2, SDN = CB + 1;  // column strides of the staging buffers (see chase_kernel)
+// Mailboxes.  A full hop (j, t) whose successor hop (j+1, t) is full as well does not write its two blocks back into
+// the band: it writes them, shifted by one row and one column, into the mailbox (j & 1, t) in exactly the layout of
+// sweep j+1's staging buffers - block below: (r, c) at [c * 64 + r], diagonal block: (row, col) at [4096 + row + 65 col]
+// (its last row is row 0 of the block below).  Staging such a hop is two contiguous TMA bulk copies issued by one
+// thread instead of ~100 cp.async per transfer thread gathering 128 band columns.  The band keeps what the mailboxes
+// do not carry: sweep 0's input, the clipped hops at the end of every sweep, column j and d[j] for hop 0.
+static constexpr int MB_B = CB * CB, MB_D = CB * SDN, MB_STRIDE = MB_B + MB_D;
 
 __device__ __forceinline__ void ll_store(unsigned long long* slot, double val, unsigned tag) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(val);
@@ -441,79 +458,54 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Transfer warps (tw = warp 0..3, cl = lane): stage the blocks of the hop at `lo` (diagonal block L x L, block below
-// L2v x L; L2v = 0: none).
-//   block below: element (r, c) lives at pdn[L + r + 127 c]; pair k of column c = rows 2k - s, 2k - s + 1 with
-//   s = (L + c) & 1 (16-byte aligned in the band) -> Bn[66 c + 2 k]; rows >= L2v and columns >= L are zero-filled.
-//   diagonal block: column col, rows col + 2k, col + 2k + 1 at pdn[128 col + 2k] -> Dn[66 col + 2k].
-static constexpr int WS_SW = 4;  // staging warps
-__device__ __forceinline__ void ws_stage_hop(const double* __restrict__ AB, int lo, int L, int L2v, double* Bn,
-                                             double* Dn, int tw, int cl) {
+// Transfer warps (tw = warp 0..3, cl = lane): stage the blocks of the hop at `lo` from the (zero-padded) band.
+//   block below: element (r, c) lives at pdn[64 + r + 127 c]; pair k of column c = rows 2k - s, 2k - s + 1 with
+//   s = c & 1 (16-byte aligned in the band) -> Bn[66 c + 2 k] (k < 32, and k = 32 for odd c: row 63 and a padding row)
+//   diagonal block: column col, rows col + 2k, col + 2k + 1 at pdn[128 col + 2k] -> Dn[66 col + 2k]; columns p and
+//   63-p hold 33 pairs together
+__device__ __forceinline__ void ws_stage_band(const double* __restrict__ AB, int lo, bool with_b, double* Bn, double* Dn,
+                                              int tw, int cl) {
   const double* const pdn = AB + (size_t)lo * LDAB;
-  if (L == CB && L2v == CB) {
-    // full blocks: no predicates (the pair of rows 63, 64 of the early-starting columns brings one padding row)
+  if (with_b) {
 #pragma unroll
-    for (int m = 0; m < (CB + WS_SW - 1) / WS_SW; ++m) {
-      const int c = tw + WS_SW * m;
-      if (c < CB) cp_async16(Bn + c * SBN + 2 * cl, pdn + CB + c * (LDAB - 1) - (c & 1) + 2 * cl, 16);
+    for (int m = 0; m < 16; ++m) {
+      const int c = tw + 4 * m;
+      cp_async16(Bn + c * SBN + 2 * cl, pdn + CB + c * (LDAB - 1) - (c & 1) + 2 * cl, 16);
     }
     if (tw == 0) {
       const int c = 2 * cl + 1;
       cp_async16(Bn + c * SBN + CB, pdn + CB + c * (LDAB - 1) - 1 + CB, 16);
     }
+  }
 #pragma unroll
-    for (int m = 0; m < (CB / 2 + WS_SW - 1) / WS_SW; ++m) {
-      const int p = tw + WS_SW * m;
-      if (p < CB / 2) {
-        const int kp = (CB - p + 1) >> 1;  // pairs of column p; column 63-p has 33 - kp
-        const int col = (cl < kp) ? p : CB - 1 - p, k = (cl < kp) ? cl : cl - kp;
-        cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
-      }
-    }
-    if (tw == 1) {  // the 33rd pair of each column pair (p, 63-p): the last pair of column 63-p
-      const int p = cl, kp = (CB - p + 1) >> 1;
-      const int col = CB - 1 - p, k = 32 - kp;
-      cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
-    }
-    return;
-  }
-  if (L2v > 0) {
-#pragma unroll 4
-    for (int m = 0; m < (CB + WS_SW - 1) / WS_SW; ++m) {
-      const int c = tw + WS_SW * m;
-      if (c >= CB) break;
-      const int s = (L + c) & 1;
-      const int r0 = 2 * cl - s;
-      int nb = 0;
-      if (c < L) nb = (r0 + 1 < L2v) ? 16 : (r0 < L2v ? 8 : 0);
-      cp_async16(Bn + c * SBN + 2 * cl, nb ? pdn + L + c * (LDAB - 1) + r0 : AB, nb);
-    }
-    if (tw == 0) {
-      // the 33rd pair (rows 63, 64) of the columns that start one element early
-      const int c = 2 * cl + ((L + 1) & 1);
-      const int nb = (c < L && CB - 1 < L2v) ? 8 : 0;
-      cp_async16(Bn + c * SBN + CB, nb ? pdn + L + c * (LDAB - 1) + (CB - 1) : AB, nb);
-    }
-  }
-#pragma unroll 4
-  for (int m = 0; m < (CB / 2 + WS_SW - 1) / WS_SW; ++m) {
-    const int p = tw + WS_SW * m;
-    if (p >= CB / 2) break;
-    const int kp = (CB - p + 1) >> 1;
+  for (int m = 0; m < 8; ++m) {
+    const int p = tw + 4 * m;
+    const int kp = (CB - p + 1) >> 1;  // pairs of column p; column 63-p has 33 - kp
     const int col = (cl < kp) ? p : CB - 1 - p, k = (cl < kp) ? cl : cl - kp;
-    const int row0 = col + 2 * k;
-    int nb = 0;
-    if (col < L) nb = (row0 + 1 < L) ? 16 : (row0 < L ? 8 : 0);
-    cp_async16(Dn + col * (SDN + 1) + 2 * k, nb ? pdn + (size_t)col * LDAB + 2 * k : AB, nb);
+    cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
   }
-  if (tw == 1) {
+  if (tw == 1) {  // the 33rd pair of each column pair: the last pair of column 63-p
     const int p = cl, kp = (CB - p + 1) >> 1;
     const int col = CB - 1 - p, k = 32 - kp;
-    const int row0 = col + 2 * k;
-    int nb = 0;
-    if (col < L) nb = (row0 + 1 < L) ? 16 : (row0 < L ? 8 : 0);
-    cp_async16(Dn + col * (SDN + 1) + 2 * k, nb ? pdn + (size_t)col * LDAB + 2 * k : AB, nb);
+    cp_async16(Dn + col * (SDN + 1) + 2 * k, pdn + (size_t)col * LDAB + 2 * k, 16);
   }
+}
+
+// Geometry of hop (j, t) in an n x n band (the band storage is zero-padded by 3 x 64 columns, so every hop computes
+// on full 64 x 64 blocks; the clipped sizes only decide which hops exist and what is stored outside the band).
+struct HopGeom {
+  int lo, L, L2;
+  bool has_b, more;
+};
+__device__ __forceinline__ bool hop_geom(int n, int j, int t, HopGeom& g) {
+  g.lo = j + 1 + t * CB;
+  if (g.lo >= n) return false;
+  g.L = min(CB, n - g.lo);
+  if (t == 0 && g.L < 2) return false;
+  g.has_b = g.lo + CB < n;
+  g.L2 = g.has_b ? min(CB, n - g.lo - CB) : 0;
+  g.more = g.has_b && g.L2 >= 2;
+  return true;
 }
 
 template <bool TRACE>
@@ -521,11 +513,12 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
   extern __shared__ __align__(16) double chase_sm[];
   double (*Ds)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chase_sm);
   double (*Bs)[CB + 1] = Ds + CB;
-  // staging of the next hop's blocks: column strides 66 / 65 and the one-element shift of the columns that start
-  // 8 bytes off make every pair of rows a 16-byte aligned copy on both sides
-  double* const Bn = chase_sm + 2 * CB * (CB + 1);  // block below: (r, c) at [c * SBN + r + ((L + c) & 1)]
-  double* const Dn = Bn + CB * SBN;                 // diagonal block, lower triangle: (row, col) at [row + col * SDN]
-  double* const colv_s = Dn + CB * SDN;             // hop 0: column j below the diagonal (CB + 2 doubles)
+  // staging of the next hop's blocks.  From a mailbox: block below (r, c) at [c * 64 + r], diagonal block (row, col) at
+  // [row + col * 65].  From the band (sweep 0, last hop of a sweep): block below at [c * 66 + r + (c & 1)] - the stride
+  // and the one-element shift of the odd columns make every pair of rows a 16-byte aligned copy on both sides.
+  double* const Bn = chase_sm + 2 * CB * (CB + 1);
+  double* const Dn = Bn + CB * SBN;
+  double* const colv_s = Dn + CB * SDN;  // hop 0: column j below the diagonal
   __shared__ double v[CB], v2[CB], w[CB], w2[CB], wa[CB];
   __shared__ double pA[2][CB], pD[2][CB], redA[4], redB[4];
   __shared__ double s_alpha, s_tau0, s_tau2;
@@ -535,9 +528,9 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
   double* AB = a.AB;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(&s_full, 32 * WS_SW);  // one deferred arrival per staging thread
-    mbar_init(&s_empty, CH_NT);   // every compute thread, once its staged numbers are in registers
-    mbar_init(&s_done, CH_NT);    // every compute thread, once its stores of the hop are issued
+    mbar_init(&s_full, 128);    // one arrival per transfer thread (deferred until its copies have landed)
+    mbar_init(&s_empty, CH_NT); // every compute thread, once its staged numbers are in registers
+    mbar_init(&s_done, CH_NT);  // every compute thread, once its stores of the hop are issued
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -553,46 +546,57 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
     unsigned h = 0;       // hops of this CTA so far: parity of s_done
     unsigned staged = 0;  // stagings issued so far: parity of s_full / s_empty
     unsigned round = 0;
-    // hop (j, t) reads what sweep j-1 had finished after ITS hop t (the late numbers travel by the slots)
-    auto stage_ready = [&](int j, int t) -> bool {
+    // Hop (j, t) reads what sweep j-1 had finished after ITS hop t (the late numbers travel by the slots).  The last
+    // hop of a sweep (no block below) reads the band, where the corner was left by sweep j-2's last hop.
+    auto stage_ready = [&](int j, int t, bool has_b) -> bool {
       if (j > 0 && ld_acquire_i32(a.prog + j - 1) < t + 1) return false;
+      if (!has_b && j > 1 && ld_acquire_i32(a.prog + j - 2) < t + 2) return false;
       if (staged > 0 && !mbar_test(&s_empty, (staged - 1) & 1u)) return false;  // previous staging still in use
       return true;
     };
-    auto stage = [&](int j, int t, int lo, int L, int L2v) {
-      ws_stage_hop(AB, lo, L, L2v, Bn, Dn, tw, cl);
-      if (t == 0 && tt < CB) {
-        const bool ok = tt < L;
-        cp_async8(colv_s + tt, ok ? AB + (1 + tt) + (size_t)j * LDAB : AB, ok ? 8 : 0);
+    auto stage = [&](int j, int t, int lo, bool has_b) {
+      const bool from_mb = j > 0 && has_b;
+      if (from_mb) {
+        if (tt == 0) {
+          const double* mb = a.mb + ((size_t)((j - 1) & 1) * a.maxhops + t) * MB_STRIDE;
+          fence_proxy_async();  // the staging buffers were read, the mailbox acquired, in the generic proxy
+          mbar_expect_tx(&s_full, (unsigned)(sizeof(double) * MB_STRIDE));
+          tma_bulk_g2s(Bn, mb, (unsigned)(sizeof(double) * MB_B), &s_full);
+          tma_bulk_g2s(Dn, mb + MB_B, (unsigned)(sizeof(double) * MB_D), &s_full);
+        }
+      } else {
+        ws_stage_band(AB, lo, has_b, Bn, Dn, tw, cl);
       }
-      cp_async_arrive_noinc(&s_full);
+      if (t == 0 && tt >= 32 && tt < 32 + CB) {  // column j (not thread 0: its arrival may have gone with expect_tx)
+        const int g = tt - 32;
+        cp_async8(colv_s + g, AB + (1 + g) + (size_t)j * LDAB, 8);  // zero beyond row n (padding)
+      }
+      if (!(from_mb && tt == 0)) cp_async_arrive_noinc(&s_full);
       ++staged;
     };
     for (int j = blockIdx.x; j < n - 2; j += gridDim.x) {
       bool any = false;
       for (int t = 0;; ++t) {
-        const int lo = j + 1 + t * CB;
-        if (lo >= n) break;
-        const int hi = min(n, lo + CB), L = hi - lo;
-        if (t == 0 && L < 2) break;
-        const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
-        const bool has_b = hi < n;
-        const bool more = has_b && (L2 >= 2);
+        HopGeom g;
+        if (!hop_geom(n, j, t, g)) break;
         any = true;
-        long long* const trp = (TRACE && j >= a.trace_j0 && j < a.trace_j0 + TR_SWEEPS && t < TR_HOPS)
-                                   ? a.trace + ((size_t)(j - a.trace_j0) * TR_HOPS + t) * TR_EV
+        long long* const trp = (TRACE && j >= a.trace_j0 && (j - a.trace_j0) % (int)gridDim.x == 0 &&
+                                    (j - a.trace_j0) / (int)gridDim.x < TR_SWEEPS && t >= a.trace_t0 && t < a.trace_t0 + TR_HOPS)
+                                   ? a.trace + ((size_t)((j - a.trace_j0) / (int)gridDim.x) * TR_HOPS + t - a.trace_t0) * TR_EV
                                    : nullptr;
+        HopGeom gn;
+        const bool have_next = g.more && hop_geom(n, j, t + 1, gn);
         int spins = 0;
         // commands: 1 publish this hop (its stores are issued), 2 stage hop 0, 3 stage the next hop, 4 give up
-        bool need_first = (t == 0), need_stage = more, need_rel = true;
+        bool need_first = (t == 0), need_stage = have_next, need_rel = true;
         while (need_first || need_stage || need_rel) {
           if (tt == 0) {
             int cmd = 0;
             if (need_first) {
-              if (stage_ready(j, 0)) cmd = 2;
+              if (stage_ready(j, 0, g.has_b)) cmd = 2;
             } else if (need_rel && mbar_test(&s_done, h & 1u)) {
               cmd = 1;
-            } else if (need_stage && stage_ready(j, t + 1)) {
+            } else if (need_stage && stage_ready(j, t + 1, gn.has_b)) {
               cmd = 3;
             }
             if (cmd == 0 && spin_giveup(spins, a.err)) cmd = 4;
@@ -603,17 +607,19 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
           ++round;
           if (cmd == 1) {
             if (tt == 0) {
-              st_release_i32(a.prog + j, more ? t + 1 : INT_MAX);
+              st_release_i32(a.prog + j, g.more ? t + 1 : INT_MAX);
               if (TRACE && trp) trp[11] = clock64();
+              CH_GSTAMP(2, j, t)
             }
             need_rel = false;
           } else if (cmd == 2) {
-            stage(j, 0, lo, L, has_b ? L2 : 0);
+            if (tt == 0) { CH_GSTAMP(3, j, 0) }
+            stage(j, 0, g.lo, g.has_b);
             need_first = false;
           } else if (cmd == 3) {
+            if (tt == 0) { CH_GSTAMP(3, j, t + 1) }
             if (TRACE && trp && tt == 0) trp[8] = clock64();
-            const int hi3 = min(n, hi2 + CB);
-            stage(j, t + 1, hi, L2, (hi2 < n) ? hi3 - hi2 : 0);
+            stage(j, t + 1, gn.lo, gn.has_b);
             if (TRACE && trp && tt == 0) trp[9] = clock64();
             need_stage = false;
           } else if (cmd == 4) {
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
           }
         }
         ++h;
-        if (!more) break;
+        if (!g.more) break;
       }
       if (!any && tt == 0) st_release_i32(a.prog + j, INT_MAX);
     }
@@ -636,235 +642,240 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
   for (int j = blockIdx.x; j < n - 2; j += gridDim.x) {
     double tau = 0.0;
     for (int t = 0;; ++t) {
-      const int lo = j + 1 + t * CB;
-      if (lo >= n) break;
-      const int hi = min(n, lo + CB), L = hi - lo;
-      if (t == 0 && L < 2) break;
-      const int hi2 = min(n, hi + CB), L2 = hi2 - hi;
-      const bool has_b = hi < n;
-      const bool more = has_b && (L2 >= 2);
-      const int Lrt = L, L2rt = L2;
-      long long* const trp = (TRACE && j >= a.trace_j0 && j < a.trace_j0 + TR_SWEEPS && t < TR_HOPS)
-                                 ? a.trace + ((size_t)(j - a.trace_j0) * TR_HOPS + t) * TR_EV
+      HopGeom g;
+      if (!hop_geom(n, j, t, g)) break;
+      const int lo = g.lo, L = g.L;
+      const bool has_b = g.has_b, more = g.more;
+      long long* const trp = (TRACE && j >= a.trace_j0 && (j - a.trace_j0) % (int)gridDim.x == 0 &&
+                                  (j - a.trace_j0) / (int)gridDim.x < TR_SWEEPS && t >= a.trace_t0 && t < a.trace_t0 + TR_HOPS)
+                                 ? a.trace + ((size_t)((j - a.trace_j0) / (int)gridDim.x) * TR_HOPS + t - a.trace_t0) * TR_EV
                                  : nullptr;
 #define CH_TRACE(ev, who) \
   if (TRACE && trp && tid == (who)) trp[ev] = clock64();
       CH_TRACE(0, 0)
-      // Late numbers: hop (j-1, t+1) exists exactly when this hop has a block below its diagonal block; it hands
-      // over the first column of its diagonal block (the corner D[63][63] and B[0 .. L2-1][63], except B[63][63]) and,
-      // when it has a block below itself (L2 = 64), the head of its bulge column (B[63][63]).  Conversely every hop
-      // t >= 1 is such a hop for the next sweep: it hands those numbers over and does not store them.
+      // Who hands what to whom:
+      //   late    hop (j-1, t+1) exists exactly when this hop has a block below its diagonal block; it hands over, through
+      //           the slots, the first column of its diagonal block (our corner D[63][63] and B[0..62][63]) and the head of
+      //           its bulge column (our B[63][63]).  Conversely every hop t >= 1 is such a hop for sweep j+1: it hands
+      //           those 65 numbers over and does not store them.
+      //   blocks  a hop with a block below takes its blocks from the mailbox of hop (j-1, t); the last hop of a sweep
+      //           (and all of sweep 0) takes them from the band.  So a hop writes into its mailbox when hop (j+1, t)
+      //           has a block below (lo + 65 < n), into the band otherwise.
       const bool late = j > 0 && has_b;
       const bool emit = t >= 1;
+      const bool from_mb = j > 0 && has_b;
+      const bool to_mb = lo + CB + 1 < n;
+      double* const mbw = a.mb + ((size_t)(j & 1) * a.maxhops + t) * MB_STRIDE;
       const unsigned long long* const ll_in =
           a.ll + ((size_t)((j + LL_RING - 1) % LL_RING) * a.maxhops + (t + 1)) * (2 * LL_PER_HOP);
       unsigned long long* const ll_out = a.ll + ((size_t)(j % LL_RING) * a.maxhops + t) * (2 * LL_PER_HOP);
       const unsigned tag_in = (unsigned)j, tag_out = (unsigned)j + 1u;
+      double* const pb = AB + (size_t)lo * LDAB + (CB + r);  // block below the diagonal block, row lo + 64 + r
+      double* const pd0 = AB + (size_t)lo * LDAB;            // diagonal block: (row, col) at pd0[row + col (LDAB-1)]
       // ---- the staged blocks of this hop have landed (also orders the v <- v2 copy of the previous hop) ------
       mbar_wait_b(&s_full, h & 1u, a.err);
       cta_sync256();
       CH_TRACE(1, 0)
-      auto hop = [&](auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
-        const int L = FULL ? CB : Lrt, L2 = FULL ? CB : L2rt;
-        double* const pb = AB + (size_t)lo * LDAB + (L + r);  // block below the diagonal block, row hi + r
-        double* const pd0 = AB + (size_t)lo * LDAB;           // diagonal block: (row, col) at pd0[row + col (LDAB-1)]
-        double x[32];
-        double colv = 0.0;
-        if (grp == 0) {
-          if (has_b) {
-  #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = cq + 2 * i;
-              x[i] = Bn[c * SBN + r + ((L + c) & 1)];  // zero outside the block
-            }
+      if (tid == 0) { CH_GSTAMP(0, j, t) }
+      double x[32];
+      double colv = 0.0;
+      if (grp == 0) {
+        if (from_mb) {
+          // mailbox layout; its last row is beyond the bulge (zero), its last column is late
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            x[i] = (r < CB - 1) ? Bn[c * CB + r] : 0.0;
           }
-          if (t == 0 && gt < L) colv = colv_s[gt];
-        } else {
-  #pragma unroll
-          for (int q = 0; q < 17; ++q) {
-            int row, col;
-            const bool ok = tri_slot(q, gw, lane, row, col) && (FULL || row < L);
-            x[q] = ok ? Dn[row + col * SDN] : 0.0;
-          }
-        }
-        mbar_arrive(&s_empty);  // this thread's staged numbers are in registers
-        if (t == 0) {
-          // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
-          if (grp == 0) {
-            double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
-            s = warp_sum(s);
-            if (lane == 0) redA[gw] = s;
-            if (gt == 0) s_alpha = colv;
-            group_bar(1);
-            double beta, tau0, scale;
-            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
-            if (gt < L) v[gt] = (gt == 0) ? 1.0 : colv * scale;
-            if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
-            if (gt == 0) {
-              AB[1 + (size_t)j * LDAB] = beta;
-              a.e[j] = beta;
-              a.d[j] = __ldcg(AB + (size_t)j * LDAB);
-              s_tau0 = tau0;
-            }
-          }
-          cta_sync256();
-          tau = s_tau0;
-        }
-        if (grp == 1) {
-          // ================= group B: two-sided update of D = A[lo:hi, lo:hi] =================================
-          if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
-          if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
-  #pragma unroll
-          for (int q = 0; q < 17; ++q) {
-            int row, col;
-            if (tri_slot(q, gw, lane, row, col) && (FULL || row < L)) {
-              Ds[row][col] = x[q];
-              Ds[col][row] = x[q];
-            }
-          }
-          group_bar(2);
-          {
-            // w = tau D v: half of the columns per thread, row r
-            double sa[4] = {0.0, 0.0, 0.0, 0.0};
-            if (r < L) {
-              const int c0 = cq * 32;
-  #pragma unroll
-              for (int c = 0; c < 31; ++c)
-                if (c0 + c < L) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
-              // late: the corner D[63][63] is the last term of row 63, so everything above runs before the hand-off
-              // has to be there
-              double dl = Ds[r][c0 + 31];
-              if (late && gt == 2 * CB - 1) {
-                dl = ll_wait(ll_in, tag_in, a.err);
-                Ds[CB - 1][CB - 1] = dl;
-              }
-              if (c0 + 31 < L) sa[3] = fma(dl, v[c0 + 31], sa[3]);
-            }
-            pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-          }
-          CH_TRACE(5, 255)
-          group_bar(2);
-          if (late && gt == 0) x[16] = Ds[CB - 1][CB - 1];  // slot 16 of thread 0 is that corner
-          {
-            const double wr0 = (gt < L) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
-            if (gt < CB) w[gt] = wr0;
-            double s = (gt < L) ? wr0 * v[gt] : 0.0;
-            s = warp_sum(s);
-            if (lane == 0) redB[gw] = s;
-          }
-          group_bar(2);
-          {
-            const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
-            if (gt < CB) w2[gt] = (gt < L) ? fma(al, v[gt], w[gt]) : 0.0;  // w + al v
-            group_bar(2);
-  #pragma unroll
-            for (int q = 0; q < 17; ++q) {
-              int row, col;
-              if (tri_slot(q, gw, lane, row, col) && (FULL || row < L)) {
-                const double val = x[q] - v[row] * w2[col] - w2[row] * v[col];
-                if (q < 2 && emit && col == 0)
-                  ll_store(ll_out + 2 * row, val, tag_out);  // first column: handed to sweep j+1, not stored
-                else
-                  pd0[row + col * (LDAB - 1)] = val;
-              }
-            }
-          }
-          CH_TRACE(6, 128)
         } else if (has_b) {
-          // ================= group A: Bk = A[hi:hi2, lo:hi] <- H2 (Bk H) and the next reflector ====================
-          {
-            double sa[4] = {0.0, 0.0, 0.0, 0.0};
-  #pragma unroll
-            for (int i = 0; i < 31; ++i) {
-              const int c = cq + 2 * i;
-              if (c < L) sa[i & 3] = fma(x[i], v[c], sa[i & 3]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cq + 2 * i;
+            x[i] = Bn[c * SBN + r + (c & 1)];
+          }
+        }
+        if (t == 0 && gt < CB) colv = colv_s[gt];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 17; ++q) {
+          int row, col;
+          x[q] = tri_slot(q, gw, lane, row, col) ? Dn[row + col * SDN] : 0.0;
+        }
+      }
+      mbar_arrive(&s_empty);  // this thread's staged numbers are in registers
+      if (t == 0) {
+        // first reflector of the sweep (group A): annihilate column j below the sub-diagonal
+        if (grp == 0) {
+          double s = (gt >= 1 && gt < L) ? colv * colv : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redA[gw] = s;
+          if (gt == 0) s_alpha = colv;
+          group_bar(1);
+          double beta, tau0, scale;
+          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau0, scale);
+          if (gt < CB) v[gt] = (gt == 0) ? 1.0 : (gt < L ? colv * scale : 0.0);
+          if (gt >= 1 && gt < L) AB[(1 + gt) + (size_t)j * LDAB] = 0.0;
+          if (gt == 0) {
+            AB[1 + (size_t)j * LDAB] = beta;
+            a.e[j] = beta;
+            a.d[j] = __ldcg(AB + (size_t)j * LDAB);
+            s_tau0 = tau0;
+          }
+        }
+        cta_sync256();
+        tau = s_tau0;
+      }
+      if (grp == 1) {
+        // ================= group B: two-sided update of D = A[lo:lo+64, lo:lo+64] ===========================
+        if (gt < L) a.VV[(size_t)(lo + gt) + (size_t)j * n] = v[gt];
+        if (gt == 0) a.TAU[t + (size_t)j * a.maxhops] = tau;
+#pragma unroll
+        for (int q = 0; q < 17; ++q) {
+          int row, col;
+          if (tri_slot(q, gw, lane, row, col)) {
+            Ds[row][col] = x[q];
+            Ds[col][row] = x[q];
+          }
+        }
+        group_bar(2);
+        {
+          // w = tau D v: half of the columns per thread, row r
+          double sa[4] = {0.0, 0.0, 0.0, 0.0};
+          const int c0 = cq * 32;
+#pragma unroll
+          for (int c = 0; c < 31; ++c) sa[c & 3] = fma(Ds[r][c0 + c], v[c0 + c], sa[c & 3]);
+          // late: the corner D[63][63] is the last term of row 63, so everything above runs before the hand-off
+          // has to be there
+          double dl = Ds[r][c0 + 31];
+          if (late && gt == 2 * CB - 1) {
+            dl = ll_wait(ll_in, tag_in, a.err);
+            Ds[CB - 1][CB - 1] = dl;
+          }
+          sa[3] = fma(dl, v[c0 + 31], sa[3]);
+          pD[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+        }
+        CH_TRACE(5, 255)
+        group_bar(2);
+        if (late && gt == 0) x[16] = Ds[CB - 1][CB - 1];  // slot 16 of thread 0 is that corner
+        {
+          const double wr0 = (gt < CB) ? tau * (pD[0][gt] + pD[1][gt]) : 0.0;
+          if (gt < CB) w[gt] = wr0;
+          double s = (gt < CB) ? wr0 * v[gt] : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redB[gw] = s;
+        }
+        group_bar(2);
+        {
+          const double al = -0.5 * tau * (redB[0] + redB[1] + redB[2] + redB[3]);
+          if (gt < CB) w2[gt] = fma(al, v[gt], w[gt]);  // w + al v
+          group_bar(2);
+#pragma unroll
+          for (int q = 0; q < 17; ++q) {
+            int row, col;
+            if (tri_slot(q, gw, lane, row, col)) {
+              const double val = x[q] - v[row] * w2[col] - w2[row] * v[col];
+              if (q < 2 && emit && col == 0)
+                ll_store(ll_out + 2 * row, val, tag_out);  // first column: handed to sweep j+1, not stored
+              else if (to_mb && col > 0)
+                mbw[MB_B + (row - 1) + (col - 1) * SDN] = val;
+              else
+                pd0[row + col * (LDAB - 1)] = val;
             }
-            // late: column 63 of the block = first column of the diagonal block of hop (j-1, t+1), rows 1..63, and the
-            // head of that hop's bulge column; it enters the sums last, so the wait sits as deep in the hop as it can
-            if (late && cq == 1 && (r < CB - 1 ? r < L2 : L2 == CB))
-              x[31] = ll_wait(ll_in + 2 * (r < CB - 1 ? r + 1 : CB), tag_in, a.err);
-            CH_TRACE(2, 64)
-            if (cq + 62 < L) sa[3] = fma(x[31], v[cq + 62], sa[3]);
+          }
+        }
+        CH_TRACE(6, 128)
+      } else if (has_b) {
+        // ================= group A: Bk = A[lo+64:lo+128, lo:lo+64] <- H2 (Bk H) and the next reflector ==========
+        {
+          double sa[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int i = 0; i < 31; ++i) sa[i & 3] = fma(x[i], v[cq + 2 * i], sa[i & 3]);
+          // late: column 63 of the block = first column of the diagonal block of hop (j-1, t+1), rows 1..63, and the
+          // head of that hop's bulge column; it enters the sums last, so the wait sits as deep in the hop as it can
+          if (late && cq == 1) x[31] = ll_wait(ll_in + 2 * (r + 1), tag_in, a.err);
+          CH_TRACE(2, 64)
+          sa[3] = fma(x[31], v[cq + 62], sa[3]);
+          pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+        }
+        group_bar(1);
+        {
+          const double ur = tau * (pA[0][r] + pA[1][r]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fma(-ur, v[cq + 2 * i], x[i]);
+        }
+        if (more) {
+          // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
+          double s = (cq == 0 && r >= 1) ? x[0] * x[0] : 0.0;
+          s = warp_sum(s);
+          if (lane == 0) redA[gw] = s;
+          if (gt == 0) s_alpha = x[0];
+          group_bar(1);
+          double beta, tau2, scale;
+          house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
+          if (cq == 0) {
+            v2[r] = (r == 0) ? 1.0 : x[0] * scale;
+            x[0] = (r == 0) ? beta : 0.0;
+          }
+          if (gt == 0) s_tau2 = tau2;
+          if (emit && gt == 0) ll_store(ll_out + 2 * CB, beta, tag_out);  // head of the new bulge column
+          CH_TRACE(3, 0)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) Bs[r][cq + 2 * i] = x[i];
+          group_bar(1);
+          {
+            // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
+            const int q0 = cq * 32;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
             pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
           }
           group_bar(1);
+          if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
+          group_bar(1);
           {
-            const double ur = tau * (pA[0][r] + pA[1][r]);
-  #pragma unroll
+            const double v2r = v2[r];
+#pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int c = cq + 2 * i;
-              if (c < L) x[i] = fma(-ur, v[c], x[i]);
+              if (c >= 1) x[i] = fma(-v2r, wa[c], x[i]);
             }
           }
-          if (more) {
-            // reflector from the first column of the bulge (held by the cq == 0 half: x[0] = Bk[r][0])
-            double s = (cq == 0 && r >= 1 && r < L2) ? x[0] * x[0] : 0.0;
-            s = warp_sum(s);
-            if (lane == 0) redA[gw] = s;
-            if (gt == 0) s_alpha = x[0];
-            group_bar(1);
-            double beta, tau2, scale;
-            house_scalars(s_alpha, redA[0] + redA[1] + redA[2] + redA[3], beta, tau2, scale);
-            if (cq == 0) {
-              if (r < L2) v2[r] = (r == 0) ? 1.0 : x[0] * scale;
-              x[0] = (r == 0) ? beta : 0.0;
-            }
-            if (gt == 0) s_tau2 = tau2;
-            if (emit && gt == 0) ll_store(ll_out + 2 * CB, beta, tag_out);  // head of the new bulge column
-            CH_TRACE(3, 0)
-  #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = cq + 2 * i;
-              if (r < L2 && c < L) Bs[r][c] = x[i];
-            }
-            group_bar(1);
-            {
-              // wa[c] = tau2 v2' Bk[:, c]: half of the rows per thread, column r (used as the column index here)
-              double sa[4] = {0.0, 0.0, 0.0, 0.0};
-              if (r < L) {
-                const int q0 = cq * 32;
-  #pragma unroll
-                for (int q = 0; q < 32; ++q)
-                  if (q0 + q < L2) sa[q & 3] = fma(v2[q0 + q], Bs[q0 + q][r], sa[q & 3]);
-              }
-              pA[cq][r] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-            }
-            group_bar(1);
-            if (gt < CB) wa[gt] = tau2 * (pA[0][gt] + pA[1][gt]);
-            group_bar(1);
-            {
-              const double v2r = (r < L2) ? v2[r] : 0.0;
-  #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int c = cq + 2 * i;
-                if (c >= 1 && c < L) x[i] = fma(-v2r, wa[c], x[i]);
-              }
-            }
-          } else if (emit && gt == 0) {
-            ll_store(ll_out + 2 * CB, x[0], tag_out);  // no further reflector: the element as the right-update left it
-          }
-  #pragma unroll
+        } else if (emit && gt == 0) {
+          ll_store(ll_out + 2 * CB, x[0], tag_out);  // no further reflector: the element as the right-update left it
+        }
+        if (to_mb) {
+          // row 0 is the last row of the next sweep's diagonal block; column 0 (the annihilated bulge column) is
+          // never read again - except its head at hop 0, which is the last entry of the next sweep's column
+#pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int c = cq + 2 * i;
-            const int dd = L + r - c;
-            if (i == 0 && emit && gt == 0) continue;  // handed over above
-            if (FULL || (r < L2 && c < L && dd < LDAB)) pb[c * (LDAB - 1)] = x[i];
+            if (c == 0) continue;
+            if (r > 0)
+              mbw[(c - 1) * CB + (r - 1)] = x[i];
+            else
+              mbw[MB_B + (CB - 1) + (c - 1) * SDN] = x[i];
           }
-          CH_TRACE(4, 0)
+          if (gt == 0 && !emit) pb[0] = x[0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i == 0 && emit && gt == 0) continue;  // handed over above
+            pb[(cq + 2 * i) * (LDAB - 1)] = x[i];
+          }
         }
-      };
-      if (L == CB && has_b && L2 == CB)
-        hop(std::true_type{});
-      else
-        hop(std::false_type{});
-      // this thread's stores of the hop are issued: the transfer warp publishes the hop once everybody is here
+        CH_TRACE(4, 0)
+      } else if (emit && gt == 0) {
+        ll_store(ll_out + 2 * CB, 0.0, tag_out);  // no block below: the head sweep j+1 waits for is a padding zero
+      }
+      // this thread's stores of the hop are issued: the transfer warps publish the hop once everybody is here
       mbar_arrive(&s_done);
+      if (tid == 0) { CH_GSTAMP(1, j, t) }
       ++h;
       cta_sync256();
       CH_TRACE(10, 0)
       if (more) {
-        if (tid < L2) v[tid] = v2[tid];
+        if (tid < CB) v[tid] = v2[tid];
         tau = s_tau2;
       }
       if (!more) break;
@@ -903,6 +914,7 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
   a.ll = nullptr;
   a.trace = nullptr;
   a.trace_j0 = 0;
+  a.trace_t0 = 0;
   DevBuf<long long> prof, trace;
   a.prof = nullptr;
   // warp-specialised kernel with the early hand-off (default); BK_CHASE_LL=0 selects the completion-flag kernel
@@ -914,17 +926,22 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
     BK_CUDA(cudaMemsetAsync(prof.p, 0, 16 * sizeof(long long), ctx->stream));
     a.prof = prof.p;
   }
-  const size_t trace_n = (size_t)TR_SWEEPS * TR_HOPS * TR_EV;
+  const size_t trace_n = (size_t)TR_SWEEPS * TR_HOPS * TR_EV + 6 * 16 * 64;  // + global-timer stamps of 16 sweeps
   if (const char* tj = getenv("BK_CHASE_TRACE")) {
     if (use_ws) {
       BK_TRY(trace.alloc(trace_n));
       BK_CUDA(cudaMemsetAsync(trace.p, 0, trace_n * sizeof(long long), ctx->stream));
       a.trace = trace.p;
       a.trace_j0 = atoi(tj);
+      a.trace_t0 = getenv("BK_CHASE_TRACE_T0") ? atoi(getenv("BK_CHASE_TRACE_T0")) : 0;
     }
   }
   DevBuf<unsigned long long> ll;
+  DevBuf<double> mbox;
+  a.mb = nullptr;
   if (use_ws) {
+    BK_TRY(mbox.alloc((size_t)2 * maxhops * MB_STRIDE));
+    a.mb = mbox.p;
     const size_t words = (size_t)LL_RING * maxhops * LL_PER_HOP * 2;
     BK_TRY(ll.alloc(words));
     BK_CUDA(cudaMemsetAsync(ll.p, 0, sizeof(unsigned long long) * words, ctx->stream));  // tag 0 = never written
@@ -965,10 +982,35 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
         const long long* e0 = h.data() + ((size_t)sj * TR_HOPS) * TR_EV;
         const long long* ev = h.data() + ((size_t)sj * TR_HOPS + th) * TR_EV;
         if (ev[0] == 0) continue;
-        fprintf(stderr, "[chase trace] %d %d", a.trace_j0 + sj, th);
+        // sweeps j0, j0 + CTAs, ... run on the same CTA: one clock; the second number is the start of the sweep
+        // relative to the first traced sweep (CTAs x the lag between neighbouring sweeps)
+        fprintf(stderr, "[chase trace] %d %d | %lld |", a.trace_j0 + sj * ctx->sm_count, th + a.trace_t0, e0[0] - h[0]);
         for (int q = 0; q < TR_EV; ++q) fprintf(stderr, " %lld", ev[q] ? ev[q] - e0[0] : -1LL);
         fprintf(stderr, "\n");
       }
+  }
+  if (a.trace) {
+    // global timer (ns) at the start of hops 0..63 of 16 consecutive sweeps: the lag between neighbours, hop by hop
+    std::vector<long long> h(trace_n);
+    BK_CUDA(cudaMemcpyAsync(h.data(), trace.p, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const long long* g = h.data() + (size_t)TR_SWEEPS * TR_HOPS * TR_EV;
+    auto G = [&](int kind, int sj, int th) { return g[((size_t)kind * 16 + sj) * 64 + th]; };
+    for (int th : {0, 1, 2, 8, 32}) {
+      fprintf(stderr, "[chase lag ns] hop %d: start(j)-start(j-1):", th);
+      for (int sj = 1; sj < 16; ++sj) fprintf(stderr, " %lld", G(0, sj, th) - G(0, sj - 1, th));
+      fprintf(stderr, "\n[chase lag ns] hop %d: per sweep j: start -> stores issued -> flag released | sweep j+1: staging "
+                      "commanded -> hop starts:", th);
+      for (int sj = 1; sj < 8; ++sj)
+        fprintf(stderr, " [%lld %lld | %lld %lld]", G(1, sj, th) - G(0, sj, th), G(2, sj, th) - G(1, sj, th),
+                G(3, sj + 1, th) - G(2, sj, th), G(0, sj + 1, th) - G(3, sj + 1, th));
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "[chase lag ns] hop 0 of sweep j+1: flag of (j,0) released -> first poll that sees it (polls so far) ; "
+                    "transfer warps waiting since (relative to the release):");
+    for (int sj = 1; sj < 8; ++sj)
+      fprintf(stderr, " [%lld (%lld) ; %lld]", G(5, sj + 1, 0) - G(2, sj, 0), G(5, sj + 1, 1), G(4, sj + 1, 0) - G(2, sj, 0));
+    fprintf(stderr, "\n");
   }
   if (a.prof) {
     long long h[16];
@@ -1350,7 +1392,9 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
   ts->maxhops = n / b + 2;
   const int npan = (int)ceil_div(n, b);
   BK_TRY(ts->work.borrow(ctx->ws[0], (size_t)n * n));
-  BK_TRY(ts->AB.alloc((size_t)LDAB * n));
+  // the band is followed by 3 x 64 zero columns: the chasing kernel computes every hop on full 64 x 64 blocks
+  BK_TRY(ts->AB.alloc((size_t)LDAB * (n + 3 * CB)));
+  BK_CUDA(cudaMemsetAsync(ts->AB.p + (size_t)LDAB * n, 0, sizeof(double) * LDAB * 3 * CB, ctx->stream));
   BK_TRY(ts->Tstore.alloc((size_t)npan * b * b));
   BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
   BK_CUDA(cudaMemsetAsync(ts->TAU.p, 0, sizeof(double) * (size_t)ts->maxhops * n, ctx->stream));
@@ -1376,7 +1420,9 @@ int twostage_reduce_dist(bk_ctx* ctx, bk_peer* peer, const double* X, long long 
   ts->maxhops = n / b + 2;
   const int npan = (int)ceil_div(n, b);
   BK_TRY(ts->work.borrow(ctx->ws[0], (size_t)n * n));
-  BK_TRY(ts->AB.alloc((size_t)LDAB * n));
+  // the band is followed by 3 x 64 zero columns: the chasing kernel computes every hop on full 64 x 64 blocks
+  BK_TRY(ts->AB.alloc((size_t)LDAB * (n + 3 * CB)));
+  BK_CUDA(cudaMemsetAsync(ts->AB.p + (size_t)LDAB * n, 0, sizeof(double) * LDAB * 3 * CB, ctx->stream));
   BK_TRY(ts->Tstore.alloc((size_t)npan * b * b));
   tm.start();
   BK_TRY(sy2sb_dist(ctx, peer, X, ldx, p, sigma, n, ts->work.p, ts->Tstore.p, ts->AB.p, LDAB, ctx->ws[2], &ts->band));
