@@ -554,16 +554,18 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
       if (staged > 0 && !mbar_test(&s_empty, (staged - 1) & 1u)) return false;  // previous staging still in use
       return true;
     };
+    // mailbox staging: thread 0 alone, at once (the other threads only add their arrivals a round later)
+    auto stage_mb = [&](int j, int t) {
+      const double* mb = a.mb + ((size_t)((j - 1) & 1) * a.maxhops + t) * MB_STRIDE;
+      fence_proxy_async();  // the staging buffers were read, the mailbox acquired, in the generic proxy
+      mbar_expect_tx(&s_full, (unsigned)(sizeof(double) * MB_STRIDE));
+      tma_bulk_g2s(Bn, mb, (unsigned)(sizeof(double) * MB_B), &s_full);
+      tma_bulk_g2s(Dn, mb + MB_B, (unsigned)(sizeof(double) * MB_D), &s_full);
+    };
     auto stage = [&](int j, int t, int lo, bool has_b) {
       const bool from_mb = j > 0 && has_b;
       if (from_mb) {
-        if (tt == 0) {
-          const double* mb = a.mb + ((size_t)((j - 1) & 1) * a.maxhops + t) * MB_STRIDE;
-          fence_proxy_async();  // the staging buffers were read, the mailbox acquired, in the generic proxy
-          mbar_expect_tx(&s_full, (unsigned)(sizeof(double) * MB_STRIDE));
-          tma_bulk_g2s(Bn, mb, (unsigned)(sizeof(double) * MB_B), &s_full);
-          tma_bulk_g2s(Dn, mb + MB_B, (unsigned)(sizeof(double) * MB_D), &s_full);
-        }
+        // thread 0 has issued the two bulk copies before it gave the command
       } else {
         ws_stage_band(AB, lo, has_b, Bn, Dn, tw, cl);
       }
@@ -591,15 +593,20 @@ __global__ void __launch_bounds__(WS_NT, 1) chase_ws_kernel(ChaseArgs a) {
         bool need_first = (t == 0), need_stage = have_next, need_rel = true;
         while (need_first || need_stage || need_rel) {
           if (tt == 0) {
+            // poll until there is something to do (the other transfer threads wait at the barrier below)
             int cmd = 0;
-            if (need_first) {
-              if (stage_ready(j, 0, g.has_b)) cmd = 2;
-            } else if (need_rel && mbar_test(&s_done, h & 1u)) {
-              cmd = 1;
-            } else if (need_stage && stage_ready(j, t + 1, gn.has_b)) {
-              cmd = 3;
+            while (cmd == 0) {
+              if (need_first) {
+                if (stage_ready(j, 0, g.has_b)) cmd = 2;
+              } else if (need_rel && mbar_test(&s_done, h & 1u)) {
+                cmd = 1;
+              } else if (need_stage && stage_ready(j, t + 1, gn.has_b)) {
+                cmd = 3;
+              }
+              if (cmd == 0 && spin_giveup(spins, a.err)) cmd = 4;
             }
-            if (cmd == 0 && spin_giveup(spins, a.err)) cmd = 4;
+            if (cmd == 2 && j > 0 && g.has_b) stage_mb(j, 0);
+            if (cmd == 3 && j > 0 && gn.has_b) stage_mb(j, t + 1);
             s_cmd[round & 1u] = cmd;
           }
           asm volatile("bar.sync 3, 128;\n" ::: "memory");
