@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(WM* WN * 32, PFC ? 3 : 0)
   constexpr int NPRE = kPrefetchC ? (BM / 2) * BN / NT : 1;
   double2 cpre[NPRE];
   const bool vecC0 = ((((uintptr_t)pr.C) & 15u) == 0) && (pr.ldc % 2 == 0);
-  const bool pre_ok = kPrefetchC && pr.prefetch_c && splits == 1 && pr.beta != 0.0 && vecC0 && (m0 + BM <= pr.m) && (n0 + BN <= pr.n);
+  const bool pre_ok = kPrefetchC && pr.prefetch_c && !pr.Cin && splits == 1 && pr.beta != 0.0 && vecC0 && (m0 + BM <= pr.m) && (n0 + BN <= pr.n);
   if (pre_ok) {
 #pragma unroll
     for (int it = 0; it < NPRE; ++it) {
@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(WM* WN * 32, PFC ? 3 : 0)
   constexpr int LDS = BM + 2;              // 2*LDS = 4 (mod 16): conflict-free fragment stores
   static_assert((size_t)CW * LDS <= (size_t)STAGES * (A_STAGE + B_STAGE), "staging tile must fit");
   double* Cs = smem;
-  const bool vecC = ((((uintptr_t)C) & 15u) == 0) && (ldc % 2 == 0);
+  // source of the read-modify-write (the same matrix unless an out-of-place update was asked for)
+  const double* Ci = (splits > 1 || !pr.Cin) ? C : pr.Cin;
+  const long long ldci = (splits > 1 || !pr.Cin) ? ldc : pr.ldcin;
+  const bool vecC = ((((uintptr_t)C) & 15u) == 0) && (ldc % 2 == 0) && ((((uintptr_t)Ci) & 15u) == 0) && (ldci % 2 == 0);
   const bool mirror = (pr.lower == 2) && (n0 + BN - 1 < m0);  // tile strictly below the diagonal
 #pragma unroll
   for (int chunk = 0; chunk < BN / CW; ++chunk) {
@@ -251,10 +254,11 @@ __global__ void __launch_bounds__(WM* WN * 32, PFC ? 3 : 0)
       if (row >= pr.m || col >= pr.n) continue;
       const double v0 = alpha * Cs[cc * LDS + 2 * rp], v1 = alpha * Cs[cc * LDS + 2 * rp + 1];
       double* cp = C + row + (long long)col * ldc;
+      const double* cip = Ci + row + (long long)col * ldci;
       if (vecC && row + 1 < pr.m) {
         double2 o = make_double2(v0, v1);
         if (beta != 0.0) {
-          const double2 old = pre_ok ? cpre[kPrefetchC ? pre_it : 0] : *reinterpret_cast<const double2*>(cp);
+          const double2 old = pre_ok ? cpre[kPrefetchC ? pre_it : 0] : *reinterpret_cast<const double2*>(cip);
           o.x += beta * old.x;
           o.y += beta * old.y;
         }
@@ -264,10 +268,10 @@ __global__ void __launch_bounds__(WM* WN * 32, PFC ? 3 : 0)
           Cs[cc * LDS + 2 * rp + 1] = o.y;
         }
       } else {
-        cp[0] = (beta != 0.0) ? v0 + beta * cp[0] : v0;
+        cp[0] = (beta != 0.0) ? v0 + beta * cip[0] : v0;
         if (mirror) Cs[cc * LDS + 2 * rp] = cp[0];
         if (row + 1 < pr.m) {
-          cp[1] = (beta != 0.0) ? v1 + beta * cp[1] : v1;
+          cp[1] = (beta != 0.0) ? v1 + beta * cip[1] : v1;
           if (mirror) Cs[cc * LDS + 2 * rp + 1] = cp[1];
         }
       }
@@ -296,7 +300,7 @@ __global__ void splitk_reduce_kernel(GemmProb pr, int splits, const double* __re
     for (int sp = 0; sp < splits; ++sp) s += ws[(size_t)sp * total + idx];
     double* c = pr.C + row + (long long)col * pr.ldc;
     double v = pr.alpha * s;
-    if (pr.beta != 0.0) v += pr.beta * (*c);
+    if (pr.beta != 0.0) v += pr.beta * (pr.Cin ? pr.Cin[row + (long long)col * pr.ldcin] : *c);
     *c = v;
   }
 }
@@ -368,8 +372,16 @@ int gemm_batched(bk_ctx* ctx, bool ta, bool tb, const GemmProb* dprobs, int npro
 int gemm(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
          long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
          int lower) {
+  return gemm_oop(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, nullptr, 0, C, ldc, lower);
+}
+
+int gemm_oop(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, long long lda,
+             const double* B, long long ldb, double beta, const double* Cin, long long ldcin, double* C, long long ldc,
+             int lower) {
   if (m <= 0 || n <= 0) return BK_OK;
   GemmProb p;
+  p.Cin = (Cin && Cin != C) ? Cin : nullptr;
+  p.ldcin = ldcin;
   p.A = A;
   p.B = B;
   p.C = C;

@@ -61,7 +61,7 @@ int eigen_full(bk_ctx* ctx, const double* K, long long ldk, int n, double* evals
 // stage 1 is GEMM-bound, stage 2 works on the L2-resident band.
 int sy2sb_bandwidth();
 int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab,
-          BandStats* stats = nullptr);
+          BandStats* stats = nullptr, const double* Ksrc = nullptr, long long ldk = 0);
 int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, double* TAU, int maxhops);
 int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int n, double* Z, long long ldz, int k);
 // GEMM-based variant for many columns (q2_blocked.cu): compact-WY blocks of 64 reflectors, batched DMMA GEMMs

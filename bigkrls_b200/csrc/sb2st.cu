@@ -1406,8 +1406,7 @@ int twostage_reduce(bk_ctx* ctx, const double* K, long long ldk, int n, TwoStage
   BK_TRY(ts->TAU.alloc((size_t)ts->maxhops * n));
   BK_CUDA(cudaMemsetAsync(ts->TAU.p, 0, sizeof(double) * (size_t)ts->maxhops * n, ctx->stream));
   tm.start();
-  BK_TRY(copy_matrix(ctx, K, ldk, n, n, 1.0, ts->work.p, n));
-  BK_TRY(sy2sb(ctx, ts->work.p, n, n, ts->Tstore.p, ts->AB.p, LDAB, &ts->band));
+  BK_TRY(sy2sb(ctx, ts->work.p, n, n, ts->Tstore.p, ts->AB.p, LDAB, &ts->band, K, ldk));
   ts->t_sy2sb = tm.stop();
   BK_TRY(ts->VV.borrow(ctx->ws[1], (size_t)n * n));
   tm.start();

@@ -16,7 +16,10 @@
 // as well) so that A22 (V T) is a plain GEMM.
 // V is left LAPACK-style below the band of A (unit diagonal implicit) and T_k is stored for the
 // back-transformation.
+#include <algorithm>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 #include "common.cuh"
 #include "dgemm.cuh"
 #include "eigen.cuh"
@@ -466,7 +469,11 @@ static int sy2sb_lookahead(bk_ctx* ctx, double* A, long long lda, int n, double*
   return BK_OK;
 }
 
-int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab, BandStats* stats) {
+// Ksrc (optional): the symmetric input matrix, read-only.  With it A need not hold a copy on entry, and for large n the
+// first part of the reduction runs as a PIPELINE (see "delayed update" below); without it A holds the matrix and
+// everything runs in place.
+int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* AB, int ldab, BandStats* stats,
+          const double* Ksrc, long long ldk) {
   const int b = SB;
   BK_REQUIRE(ldab >= 2 * b, "sy2sb: band storage needs 2b rows");
   if (const char* la = getenv("BK_SY2SB_LOOKAHEAD"))
@@ -494,7 +501,8 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
   static const bool full_update = getenv("BK_SY2SB_FULL") != nullptr;
   // CUDA events around the two large GEMMs of every panel (roofline of the dominant kernel, bench.py)
   // (events come from the context's pool: created once, reused by every fit)
-  size_t n_ev = 2;
+  size_t n_ev = 16;  // 0..15: ordering events of the pipelined phase; then start/end pairs of the large GEMMs
+  const size_t ev0 = n_ev;
   double flops = 0.0;
   auto mark = [&]() {
     if (!stats) return;
@@ -568,9 +576,146 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
     return finish_w_fused(ctx, n, r0, Vd, Wd, Wd2, Tk, S2.p, S3.p);
   };
 
-  int k = 0, pair = 0;
+  int k = 0, pair = 0, c_start = 0;
+  // ---- Delayed update (pipelined phase, large trailing matrices) -------------------------------------------------
+  // In place, the two panel factorisations of a pair, their small GEMMs and the big products Z = A22 (V T) all wait for
+  // the rank-256 update of the previous pair, and the update waits for them: per pair ~0.75 ms of latency-bound work
+  // with the tensor pipe idle.  Here the chain of pair i does not wait for the update U_{i-1}: it works on the matrix as
+  // it was BEFORE that update, A^(i-1), and corrects for it with skinny products:
+  //     columns of the pair:  A^(i)[:, cols] = A^(i-1)[:, cols] - PA_{i-1} PB_{i-1}[cols]'             (into A)
+  //     Z = A^(i) X           = A^(i-1) X - PA_{i-1} (PB_{i-1}' X)
+  // while U_{i-1}: A^(i) = A^(i-1) - PA_{i-1} PB_{i-1}' runs on the other stream OUT OF PLACE into the second of two
+  // work matrices (nobody overwrites what the chain still reads).  The chain runs on the high-priority stream; the
+  // update fills the machine whenever the chain leaves it idle.  A receives only the factored panels (what the band
+  // extraction and the back-transformation read); the last update of the phase writes the trailing matrix into A and
+  // the in-place loop below takes over (small matrices are latency-bound either way, and there both panels of a pair
+  // would be exposed).
+  // (read per call: the tests run both variants in one process)
+  const int pipe_min = getenv("BK_SY2SB_PIPE_MIN") ? atoi(getenv("BK_SY2SB_PIPE_MIN")) : 10240;
+  const bool no_pipe = getenv("BK_SY2SB_NOPIPE") != nullptr;
+  bool piped = Ksrc && pair_panels && !full_update && !no_pipe && (n - 3 * b >= pipe_min) && pipe_min >= 4 * b;
+  if (piped) {
+    DevBuf<double> W0, W1, Gs4;
+    BK_TRY(W0.borrow(ctx->ws[2], (size_t)n * n));
+    BK_TRY(W1.borrow(ctx->ws[3], (size_t)n * n));
+    BK_TRY(Gs4.alloc((size_t)4 * b * b));
+    double* Wb[2] = {W0.p, W1.p};
+    // A^(m) lives in: the input for m = 0, else work matrix (m-1) & 1
+    auto base_of = [&](int mth, long long& ld) -> const double* {
+      if (mth == 0) {
+        ld = ldk;
+        return Ksrc;
+      }
+      ld = n;
+      return Wb[(mth - 1) & 1];
+    };
+    auto e_chain = [&](int i) { return pool_event(ctx, 2 + (i & 3)); };
+    auto e_upd = [&](int i) { return pool_event(ctx, 6 + (i & 3)); };
+    cudaEvent_t e_begin = pool_event(ctx, 10);
+    BK_CUDA(cudaEventRecord(e_begin, main_st));
+    BK_CUDA(cudaStreamWaitEvent(side_st, e_begin, 0));
+    // BK_SY2SB_PIPE_TRACE=i0: start/end of the chain and of the update of pairs i0..i0+7, relative to the phase's start
+    const int tr_i0 = getenv("BK_SY2SB_PIPE_TRACE") ? atoi(getenv("BK_SY2SB_PIPE_TRACE")) : -1;
+    std::vector<cudaEvent_t> trev;
+    if (tr_i0 >= 0) {
+      trev.resize(8 * 6);
+      for (auto& e : trev) cudaEventCreate(&e);
+    }
+    auto trace_ev = [&](int i, int which, cudaStream_t st) {
+      if (tr_i0 >= 0 && i >= tr_i0 && i < tr_i0 + 8) cudaEventRecord(trev[(size_t)(i - tr_i0) * 6 + which], st);
+    };
+    int i = 0;
+    for (;; ++i) {
+      const int c0 = 2 * b * i, r0 = c0 + b, r1 = r0 + b, r2 = r1 + b;
+      const int m = n - r0, m2 = n - r1, m3 = n - r2;
+      double* PA = PAbuf.p + (size_t)(i & 1) * 4 * blk;
+      double* PB = PBbuf.p + (size_t)(i & 1) * 4 * blk;
+      const double* PAp = PAbuf.p + (size_t)((i + 1) & 1) * 4 * blk;  // the pending pair i-1
+      const double* PBp = PBbuf.p + (size_t)((i + 1) & 1) * 4 * blk;
+      double* T1 = Tstore + (size_t)(2 * i) * b * b;
+      double* T2 = T1 + (size_t)b * b;
+      long long ldp = 0, ldi = 0;
+      const double* Bp = base_of(i > 0 ? i - 1 : 0, ldp);  // A^(i-1) (i = 0: the input itself, nothing pending)
+      const bool last = (m3 - 2 * b < pipe_min);           // the next pair is left to the in-place loop
+      {
+        SideStreamScope sc(ctx);
+        if (i >= 2) BK_CUDA(cudaStreamWaitEvent(side_st, e_upd(i - 2), 0));  // A^(i-1) is complete
+        trace_ev(i, 0, side_st);
+        // columns of both panels (rows c0.., diagonal blocks included) into A
+        if (i == 0)
+          BK_TRY(copy_matrix(ctx, Ksrc, ldk, n, 2 * b, 1.0, A, lda));
+        else
+          BK_TRY(gemm_oop(ctx, false, true, n - c0, 2 * b, 4 * b, -1.0, PAp + c0, n, PBp + c0, n, 1.0,
+                          Bp + c0 + (long long)c0 * ldp, ldp, A + c0 + (long long)c0 * lda, lda));
+        // ---- first panel
+        BK_TRY(factor_panel(c0, PA, PB + blk, T1));
+        mark();
+        BK_TRY(gemm(ctx, false, false, m, b, m, 1.0, Bp + r0 + (long long)r0 * ldp, ldp, VT.p, m, 0.0, PA + blk + r0, n));
+        mark();
+        flops += 2.0 * m * (double)m * b;
+        if (i > 0) {
+          BK_TRY(gemm(ctx, true, false, 4 * b, b, m, 1.0, PBp + r0, n, VT.p, m, 0.0, Gs4.p, 4 * b));
+          BK_TRY(gemm(ctx, false, false, m, b, 4 * b, -1.0, PAp + r0, n, Gs4.p, 4 * b, 1.0, PA + blk + r0, n));
+        }
+        BK_TRY(finish_w(r0, PA, PA + blk, PB, T1));
+        trace_ev(i, 1, side_st);
+        // ---- second panel: its columns get the first panel's update, then as above with one more correction
+        BK_TRY(gemm(ctx, false, true, m, b, 2 * b, -1.0, PA + r0, n, PB + r0, n, 1.0, A + r0 + (long long)r0 * lda, lda));
+        BK_TRY(factor_panel(r0, PA + 2 * blk, PB + 3 * blk, T2));
+        mark();
+        BK_TRY(gemm(ctx, false, false, m2, b, m2, 1.0, Bp + r1 + (long long)r1 * ldp, ldp, VT.p, m2, 0.0, PA + 3 * blk + r1, n));
+        mark();
+        flops += 2.0 * m2 * (double)m2 * b;
+        if (i > 0) {
+          BK_TRY(gemm(ctx, true, false, 4 * b, b, m2, 1.0, PBp + r1, n, VT.p, m2, 0.0, Gs4.p, 4 * b));
+          BK_TRY(gemm(ctx, false, false, m2, b, 4 * b, -1.0, PAp + r1, n, Gs4.p, 4 * b, 1.0, PA + 3 * blk + r1, n));
+        }
+        BK_TRY(gemm(ctx, true, false, 2 * b, b, m2, 1.0, PB + r1, n, VT.p, m2, 0.0, Gs.p, 2 * b));
+        BK_TRY(gemm(ctx, false, false, m2, b, 2 * b, -1.0, PA + r1, n, Gs.p, 2 * b, 1.0, PA + 3 * blk + r1, n));
+        BK_TRY(finish_w(r1, PA + 2 * blk, PA + 3 * blk, PB + 2 * blk, T2));
+        trace_ev(i, 2, side_st);
+        BK_CUDA(cudaEventRecord(e_chain(i), side_st));
+      }
+      // ---- U_i on the main stream: A^(i+1) = A^(i) - PA PB' on the trailing block, out of place
+      BK_CUDA(cudaStreamWaitEvent(main_st, e_chain(i), 0));
+      const double* Bi = base_of(i, ldi);
+      double* Cout = last ? A + r2 + (long long)r2 * lda : Wb[i & 1] + r2 + (long long)r2 * n;
+      const long long ldo = last ? lda : (long long)n;
+      trace_ev(i, 3, main_st);
+      mark();
+      BK_TRY(gemm_oop(ctx, false, true, m3, m3, 4 * b, -1.0, PA + r2, n, PB + r2, n, 1.0, Bi + r2 + (long long)r2 * ldi, ldi,
+                      Cout, ldo, 2));
+      mark();
+      flops += 1.0 * m3 * (double)m3 * 4 * b;
+      trace_ev(i, 4, main_st);
+      if (last) {
+        // the first panel's columns of the next pair (rows r1.., its diagonal block included) with this pair's update
+        BK_TRY(gemm_oop(ctx, false, true, m2, b, 4 * b, -1.0, PA + r1, n, PB + r1, n, 1.0, Bi + r1 + (long long)r1 * ldi, ldi,
+                        A + r1 + (long long)r1 * lda, lda));
+        ++i;
+        break;
+      }
+      BK_CUDA(cudaEventRecord(e_upd(i), main_st));
+    }
+    if (tr_i0 >= 0) {
+      cudaStreamSynchronize(main_st);
+      cudaStreamSynchronize(side_st);
+      for (int q = 0; q < 8 && tr_i0 + q < i; ++q) {
+        float t[5];
+        for (int w = 0; w < 5; ++w) cudaEventElapsedTime(&t[w], e_begin, trev[(size_t)q * 6 + w]);
+        fprintf(stderr, "[sy2sb pipe] pair %d (m = %d): chain %.3f .. panel 2 at %.3f .. %.3f ms | update %.3f .. %.3f ms\n", tr_i0 + q,
+                n - (2 * b * (tr_i0 + q) + b), t[0], t[1], t[2], t[3], t[4]);
+      }
+      for (auto& e : trev) cudaEventDestroy(e);
+    }
+    c_start = 2 * b * i;
+    k = 2 * i;
+    pair = i;
+  } else if (Ksrc) {
+    BK_TRY(copy_matrix(ctx, Ksrc, ldk, n, n, 1.0, A, lda));
+  }
   bool ahead = false;  // the first panel of this pair was factored on the side stream during the previous update
-  for (int c0 = 0; c0 < n; ++pair) {
+  for (int c0 = c_start; c0 < n; ++pair) {
     const int r0 = c0 + b, m = n - r0;
     if (m < 2) break;
     double* PA = PAbuf.p + (size_t)(pair & 1) * 4 * blk;
@@ -656,14 +801,32 @@ int sy2sb(bk_ctx* ctx, double* A, long long lda, int n, double* Tstore, double* 
             h[4], h[0] / nc, h[1] / nc, h[2] / nc, h[3] / nc);
   }
   if (stats) {
-    double sec = 0.0;
-    for (size_t i = 2; i + 1 < n_ev; i += 2) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, ctx->event_pool[i], ctx->event_pool[i + 1]);
-      sec += ms * 1e-3;
+    // time during which at least one of the large GEMMs ran (in the pipelined phase products and updates overlap on two
+    // streams: their intervals are merged, not added)
+    std::vector<std::pair<double, double>> iv;
+    for (size_t i = ev0; i + 1 < n_ev; i += 2) {
+      float s0 = 0.f, s1 = 0.f;
+      cudaEventElapsedTime(&s0, ctx->event_pool[ev0], ctx->event_pool[i]);
+      cudaEventElapsedTime(&s1, ctx->event_pool[ev0], ctx->event_pool[i + 1]);
+      iv.emplace_back((double)s0, (double)s1);
     }
-    stats->gemm_launches = (double)((n_ev - 2) / 2);
-    stats->gemm_seconds = sec;
+    std::sort(iv.begin(), iv.end());
+    double sec = 0.0, cur_s = 0.0, cur_e = -1.0;
+    for (auto& x : iv) {
+      if (cur_e < 0.0) {
+        cur_s = x.first;
+        cur_e = x.second;
+      } else if (x.first <= cur_e) {
+        cur_e = std::max(cur_e, x.second);
+      } else {
+        sec += cur_e - cur_s;
+        cur_s = x.first;
+        cur_e = x.second;
+      }
+    }
+    if (cur_e >= 0.0) sec += cur_e - cur_s;
+    stats->gemm_launches = (double)((n_ev - ev0) / 2);
+    stats->gemm_seconds = sec * 1e-3;
     stats->gemm_flops = flops;
   }
   return BK_OK;

@@ -56,6 +56,34 @@ def test_twostage(ctx, n, p, k):
     assert orth < 1e-12 * np.sqrt(n), orth
 
 
+@pytest.mark.parametrize("n,pipe_min", [(1000, 256), (1531, 512), (3001, 512), (3001, 2048), (4608, 1024)])
+def test_sy2sb_delayed_update_pipeline(ctx, monkeypatch, n, pipe_min):
+    """The pipelined phase of the dense->band stage (chain of pair i on the matrix BEFORE the previous pair's update,
+    corrected with skinny products; updates out of place on the other stream) forced at small n: tridiagonal spectrum
+    against LAPACK, and the back-transformed vectors diagonalise K (they go through the panels the phase deposits)."""
+    lib = _lib.load()
+    A = kernel_matrix(n, 5)
+    ref = np.linalg.eigvalsh(A)
+    monkeypatch.setenv("BK_SY2SB_PIPE_MIN", str(pipe_min))
+    d = np.zeros(n)
+    e = np.zeros(n)
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), None, 0, None))
+    lam, S = eigh_tridiagonal(d, e[:n - 1])
+    assert np.max(np.abs(lam - ref)) < 1e-12 * ref.max()
+    k = 64
+    Z = np.asfortranarray(S[:, n - k:])
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d), dptr(e), dptr(Z), k, None))
+    assert np.max(np.abs(A @ Z - Z * lam[n - k:])) < 1e-12 * ref.max() * np.sqrt(n)
+    assert np.max(np.abs(Z.T @ Z - np.eye(k))) < 1e-12 * np.sqrt(n)
+    # and against the in-place loop alone
+    monkeypatch.setenv("BK_SY2SB_NOPIPE", "1")
+    d0 = np.zeros(n)
+    e0 = np.zeros(n)
+    check(lib.bk_debug_twostage(ctx.handle, dptr(A), n, None, dptr(d0), dptr(e0), None, 0, None))
+    lam0 = eigh_tridiagonal(d0, e0[:n - 1], eigvals_only=True)
+    assert np.max(np.abs(lam - lam0)) < 1e-12 * ref.max()
+
+
 @pytest.mark.parametrize("n", [130, 193, 200, 257, 517, 1000, 3001, 6007])
 def test_chase_handoff_protocols_agree_bitwise(ctx, monkeypatch, n):
     """The early hand-off kernel (tagged slots + staged blocks, sb2st.cu) runs the same arithmetic as the
