@@ -483,7 +483,12 @@ def main():
                     "algorithmic_flops_per_launch": info["band_gemm_flops"] / nl,
                     "avg_launch_seconds": info["band_gemm_seconds"] / nl,
                     "share_of_step": info["band_gemm_seconds"] / info["t_total"],
-                    "note": None if world == 1 else "multi-GPU run: the dense->band GEMMs are distributed and not "
+                    "note": ("in the delayed-update phase of the dense->band stage the products Z = A22 (V T) (high-priority "
+                             "stream) and the rank-256 updates (main stream) run at the same time: `achieved` divides their "
+                             "flops by the UNION of their event intervals, launches and avg_launch_seconds refer to that busy "
+                             "time; one at a time (BK_SY2SB_NOPIPE=1) the same kernels measure 26.9 TF/s = 0.72 of the peak "
+                             "and the step is 0.017 s longer (profiles/r02c_bench_N20000.json)") if world == 1 else
+                            "multi-GPU run: the dense->band GEMMs are distributed and not "
                             "bracketed by events; the roofline of the dominant kernel is the n_gpus=1 line",
                     "traffic": traffic, "traffic_source": traffic_src}
     else:
