@@ -1034,9 +1034,9 @@ int sb2st(bk_ctx* ctx, double* AB, int n, double* d, double* e, double* VV, doub
 // ---------------------------------------------------------------------------------------------------------
 // Q2 back-transformation on Zt (k x n, row r of Z = column r of Zt, contiguous)
 // ---------------------------------------------------------------------------------------------------------
-static constexpr int Q2_KC = 160;           // columns of Z per launch
-static constexpr int Q2_CT = 2 * Q2_KC;     // compute threads: two per column (upper / lower half of the window)
-static constexpr int Q2_NT = Q2_CT + 32;    // + one warp that only polls / publishes the pipeline flags
+static constexpr int Q2_KC = 160;           // columns of Z per launch (widest variant of the kernel)
+// per variant: 2 WC compute threads, two per column (upper / lower half of the window), + one warp that only polls /
+// publishes the pipeline flags
 static constexpr int Q2_R = 4;              // sweeps applied per pass over the window
 static constexpr int Q2_HALF = 34;          // window rows per thread: 2 * 34 >= 64 + Q2_R - 1
 static constexpr int Q2_ROWS = 112;         // buffer rows: the window slides through the buffer, no wrap-around
@@ -1066,7 +1066,13 @@ struct Q2Args {
 //   shared memory, one thread per column.
 // Rows retired by hop index t-1 are the rows entering the window of hop index t: done[t-1] is the only
 // synchronisation between CTAs (acquire/release, one warp of each CTA does nothing else).
-__global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
+// WC = columns per launch (row stride of the window buffer).  160 for wide blocks (one CTA per SM, one launch per
+// 160 columns); 80 / 48 for the narrow blocks a rank gets when the back-transformation is split over 4 / 8 GPUs: less
+// shared memory and fewer threads per CTA let 2 / 3 CTAs share an SM, so that every hop index has its own CTA and
+// the pipeline over hop indices is not run twice per CTA.
+template <int WC>
+__global__ void __launch_bounds__(2 * WC + 32, (WC <= 48) ? 3 : (WC <= 80 ? 2 : 1)) q2_apply_kernel(Q2Args a) {
+  constexpr int Q2_KC = WC, Q2_CT = 2 * WC, Q2_NT = Q2_CT + 32;
   extern __shared__ __align__(16) double win[];  // Q2_ROWS x Q2_KC
   __shared__ __align__(16) double vsx[2][Q2_R][2][Q2_HALF];  // zero-padded reflectors of a pass, per half
   __shared__ double taus[2][Q2_R];
@@ -1143,16 +1149,24 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
     const bool fast_phase = (j >= Q2_R - 1);
     if (fast_phase) {
       // loads for a pass starting at sweep jp: its 4 new rows (two per half-thread) and its 4 reflectors
-      double pr[2], vreg = 0.0, treg = 0.0;
+      constexpr int NVE = Q2_R * 2 * Q2_HALF;             // reflector entries of a pass
+      constexpr int NV = (NVE + Q2_NT - 1) / Q2_NT;        // per thread (1 for the wide variant)
+      double pr[2], vreg[NV], treg = 0.0;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) vreg[q] = 0.0;
       auto issue_pass_loads = [&](int jp) {
         const int lo = jp + 1 + t * CB;
         pr[0] = act ? __ldcg(a.Zt + col + (size_t)(lo - 2 * h) * a.ldzt) : 0.0;
         pr[1] = act ? __ldcg(a.Zt + col + (size_t)(lo - 2 * h - 1) * a.ldzt) : 0.0;
-        if (tid < Q2_R * 2 * Q2_HALF) {
-          // zero-padded reflector s on the pass window: window index i <-> row lo-3+i, reflector rows lo-s ..
-          const int s = tid / (2 * Q2_HALF), i = tid % (2 * Q2_HALF);
-          const int vi = i - (Q2_R - 1 - s);
-          vreg = (vi >= 0 && vi < CB && lo - s + vi < n) ? VV[(size_t)(lo - s + vi) + (size_t)(jp - s) * n] : 0.0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int e = tid + q * Q2_NT;
+          if (e < NVE) {
+            // zero-padded reflector s on the pass window: window index i <-> row lo-3+i, reflector rows lo-s ..
+            const int s = e / (2 * Q2_HALF), i = e % (2 * Q2_HALF);
+            const int vi = i - (Q2_R - 1 - s);
+            vreg[q] = (vi >= 0 && vi < CB && lo - s + vi < n) ? VV[(size_t)(lo - s + vi) + (size_t)(jp - s) * n] : 0.0;
+          }
         }
         if (tid < Q2_R) treg = a.TAU[t + (size_t)(jp - tid) * a.maxhops];
       };
@@ -1161,7 +1175,11 @@ __global__ void __launch_bounds__(Q2_NT, 1) q2_apply_kernel(Q2Args a) {
           colp[(pn - 2 * h) * Q2_KC] = pr[0];
           colp[(pn - 2 * h - 1) * Q2_KC] = pr[1];
         }
-        if (tid < Q2_R * 2 * Q2_HALF) (&vsx[buf][0][0][0])[tid] = vreg;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int e = tid + q * Q2_NT;
+          if (e < NVE) (&vsx[buf][0][0][0])[e] = vreg[q];
+        }
         if (tid < Q2_R) taus[buf][tid] = treg;
       };
       // a pass at sweep jp needs hop index t-1 to have applied sweep jp-2
@@ -1294,8 +1312,15 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
   const int KC = (int)ceil_div(k, nchunk);  // balanced column chunks, each <= Q2_KC
   BK_TRY(Zt.alloc((size_t)KC * n));
   BK_TRY(done.alloc(nhop));
-  BK_CUDA(cudaFuncSetAttribute(q2_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(double) * Q2_ROWS * Q2_KC)));
+  // kernel variant by chunk width; CTAs that can be resident at once (the pipeline over hop indices needs them all)
+  const int wc = (KC <= 48) ? 48 : (KC <= 80 ? 80 : Q2_KC);
+  void* kern = (wc == 48) ? (void*)q2_apply_kernel<48> : (wc == 80 ? (void*)q2_apply_kernel<80> : (void*)q2_apply_kernel<Q2_KC>);
+  const size_t smem = sizeof(double) * Q2_ROWS * wc;
+  const int nthreads = 2 * wc + 32;
+  BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
+  per_sm = std::max(1, per_sm);
   for (int k0 = 0; k0 < k; k0 += KC) {
     const int kc = std::min(KC, k - k0);
     dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(kc, 32));
@@ -1320,9 +1345,8 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
       a.prof = prof.p;
     }
     void* kargs[] = {&a};
-    const int G = std::min(ctx->sm_count, nhop);
-    BK_CUDA(cudaLaunchCooperativeKernel((void*)q2_apply_kernel, dim3(G), dim3(Q2_NT), kargs,
-                                        sizeof(double) * Q2_ROWS * Q2_KC, ctx->stream));
+    const int G = std::min(ctx->sm_count * per_sm, nhop);
+    BK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(nthreads), kargs, smem, ctx->stream));
     BK_LAUNCHED(ctx);
     dim3 tg2((unsigned)ceil_div(kc, 32), (unsigned)ceil_div(n, 32));
     transpose_kernel<<<tg2, 256, 0, ctx->stream>>>(Zt.p, kc, kc, n, Z + (size_t)k0 * ldz, ldz);

@@ -31,7 +31,7 @@ def band_to_dense(band, n, b):
 
 
 @pytest.mark.parametrize("n,p,k", [(3, 3, 3), (66, 3, 66), (130, 3, 130), (517, 6, 100), (1000, 4, 1000),
-                                    (3001, 5, 400)])
+                                    (3001, 5, 400), (3001, 5, 36), (4608, 5, 72), (2500, 4, 17)])
 def test_twostage(ctx, n, p, k):
     lib = _lib.load()
     A = kernel_matrix(n, p)
