@@ -402,7 +402,12 @@ int gemm_oop(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, c
   p.stagger_slots = 0;
 
   int bm, bn;
-  if (n <= 32) {
+  if (n <= 24 && n > 16) {
+    // the K-pass of the marginal effects (n = 2P + 2 = 22 at P = 10): three 8-wide DMMA tiles instead of four, a
+    // quarter of the tensor work of the 32-wide tile was padding
+    bm = 128;
+    bn = 24;
+  } else if (n <= 32) {
     bm = 128;
     bn = 32;
   } else if (m <= 64) {
@@ -422,7 +427,8 @@ int gemm_oop(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, c
   }
   if (const char* f = getenv("BK_GEMM_FORCE")) {  // tuning experiments only
     int fm = 0, fn = 0;
-    if (sscanf(f, "%dx%d", &fm, &fn) == 2 && ((fm == 128 && (fn == 128 || fn == 64 || fn == 32)) || (fm == 64 && fn == 64))) {
+    if (sscanf(f, "%dx%d", &fm, &fn) == 2 && ((fm == 128 && (fn == 128 || fn == 64 || fn == 32)) || (fm == 64 && fn == 64)) &&
+        !(fn < n && fn <= 32)) {
       bm = fm;
       bn = fn;
     }
@@ -432,7 +438,7 @@ int gemm_oop(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, c
   // chosen against wave quantisation: tiles * splits CTAs run in waves of (resident CTAs per SM) * SMs, and a
   // last wave that is 10 % full costs as much as a full one (e.g. 157 tiles x 4 splits on 296 slots = 2.12 waves).
   int splits = 1;
-  const int resident = (bm == 128 && bn == 128) ? 1 : (bm == 64 ? 3 : 2);
+  const int resident = (bm == 128 && bn == 128) ? 1 : (bm == 64 ? 3 : 2);  // (the narrow 128 x 24 / 32 tiles: >= 2)
   const int slots = resident * ctx->sm_count;
   if (!lower && tiles < 8 * slots && k >= 1024) {
     const int smax = (int)std::max<int64_t>(1, std::min<int64_t>(64, k / 256));
@@ -471,6 +477,8 @@ int gemm_oop(bk_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, c
   // first wave, no effect - the CTAs of an SM are not phase-locked.)
   if (bm == 64 && bn == 64 && !ta && tb && vec && splits == 1 && beta != 0.0 && k <= 128 && p.prefetch_c)
     rc = launch_one<64, 64, 2, 4, false, true, true, 3, true>(ctx, p, nullptr, 1, tiles, splits, ws);
+  else if (bn == 24)
+    rc = dispatch<128, 24, 8, 1>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
   else if (bn == 32)
     rc = dispatch<128, 32, 8, 1>(ctx, ta, tb, vec, p, nullptr, 1, tiles, splits, ws);
   else if (bm == 128 && bn == 64)

@@ -89,7 +89,62 @@ double ratio_sum_fast(const std::vector<double>& ev, double x, double* abs_terms
 // sign of (R's sum(ev/(ev+x)) - thr): -1 below, 0 equal, +1 above.  Decided by the fast sum whenever it is
 // further from the threshold than its own error bound (plus the long-double sum's), otherwise by the reference's
 // arithmetic itself - so every comparison of the bounds loops has exactly the outcome R would get.
+// Most of a kernel matrix's spectrum is rounding noise around zero: for |e| <= 1e-10 x the term e/(e+x) equals e/x up
+// to a relative 2e-10, so the tail of the (descending) spectrum enters the fast sums through suffix sums of e and |e|
+// and only the leading part is divided out - a few hundred terms instead of Neig.  The tail's truncation error joins
+// the error band of the comparison, so the decisions stay exactly R's.
+struct RatioTail {
+  const std::vector<double>* ev = nullptr;
+  bool sorted = false;
+  std::vector<double> s1, a1;  // suffix sums of e and |e|
+  void build(const std::vector<double>& e) {
+    ev = &e;
+    const size_t n = e.size();
+    sorted = true;
+    for (size_t i = 1; i < n && sorted; ++i) sorted = e[i] <= e[i - 1];
+    if (!sorted) return;
+    s1.assign(n + 1, 0.0);
+    a1.assign(n + 1, 0.0);
+    for (size_t i = n; i-- > 0;) {
+      s1[i] = s1[i + 1] + e[i];
+      a1[i] = a1[i + 1] + std::fabs(e[i]);
+    }
+  }
+  // first index whose value (and, the spectrum being descending, every later POSITIVE value) is below 1e-10 x; the
+  // negative noise behind it must be as small in magnitude for the expansion to hold: checked on the last element
+  size_t cut(double x) const {
+    const std::vector<double>& e = *ev;
+    if (!sorted || !(x > 0.0) || e.empty() || std::fabs(e.back()) > 1e-10 * x) return e.size();
+    size_t lo = 0, hi = e.size();
+    while (lo < hi) {
+      const size_t mid = lo + (hi - lo) / 2;
+      if (e[mid] < 1e-10 * x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  }
+};
+thread_local RatioTail g_tail;
+
 int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
+  if (g_tail.ev == &ev && g_tail.sorted) {
+    const size_t c = g_tail.cut(x);
+    if (c < ev.size()) {
+      double s[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+      for (size_t i = 0; i < c; ++i) {
+        const double t = ev[i] / (ev[i] + x);
+        s[i & 3] += t;
+        a[i & 3] += std::fabs(t);
+      }
+      const double tail = g_tail.s1[c] / x, tail_abs = g_tail.a1[c] / x;
+      const double f = ((s[0] + s[1]) + (s[2] + s[3])) + tail;
+      const double at = ((a[0] + a[1]) + (a[2] + a[3])) + tail_abs;
+      const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 4 + 8) * at + 4e-10 * tail_abs +
+                          1e-13 * std::fabs(thr);
+      if (std::isfinite(f) && std::fabs(f - thr) > band) return f < thr ? -1 : 1;
+      const double sx = (double)ratio_sum(ev, x);
+      return sx < thr ? -1 : (sx > thr ? 1 : 0);
+    }
+  }
   double at = 0.0;
   const double f = ratio_sum_fast(ev, x, &at);
   const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 8 + 8) * at + 1e-13 * std::fabs(thr);
@@ -103,12 +158,18 @@ int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
 // the reference's own comparisons.
 double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
   double x = x0;
+  const bool tail_ok = g_tail.ev == &ev && g_tail.sorted;
   for (int it = 0; it < 12; ++it) {
     double f = 0.0, g = 0.0;
-    for (double e : ev) {
-      const double d = e + x, r = e / d;
+    const size_t c = tail_ok ? g_tail.cut(x) : ev.size();
+    for (size_t i = 0; i < c; ++i) {
+      const double e = ev[i], d = e + x, r = e / d;
       f += r;
       g -= r / d;
+    }
+    if (c < ev.size()) {  // the noise tail: e/(e+x) ~ e/x (a starting guess only)
+      f += g_tail.s1[c] / x;
+      g -= g_tail.s1[c] / (x * x);
     }
     if (!(g < 0.0) || !std::isfinite(f)) break;
     const double xn = x - (f - thr) / g;
@@ -123,6 +184,10 @@ double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
 }
 
 int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
+  g_tail.build(ev);
+  struct TailReset {
+    ~TailReset() { g_tail.ev = nullptr; }
+  } tail_reset;
   if (!(*U > 0.0)) {
     // Reference (R/bigKRLS_Rcpp_functions.R:16-20): U = n; while (sum(ev/(ev+U)) < 1) U = U - 1 - hundreds to
     // thousands of O(Neig) sums.  f(U) = sum(ev/(ev+U)) is strictly decreasing with f(U) - f(U+1) ~ 1/U, many

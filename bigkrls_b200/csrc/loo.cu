@@ -7,9 +7,11 @@
 // read of Q (8nk bytes) serves every candidate, which is what makes the speculative
 // golden-section tree (fit.cu) cost one pass per 3 iterations.
 //
-// Kernel 1: thread = row, CTA = 256 rows x one k-slice; the 2L weight columns of the slice
-//           are staged in shared memory (broadcast reads), Q is read coalesced along rows,
-//           2L FP64 FMAs per loaded element.  Partials go to a [ksplit][2L][rows] buffer.
+// Kernel 1: thread = two rows, CTA = 512 rows x one k-slice; the 2L weight columns of the slice
+//           are staged in shared memory (broadcast 16-byte reads: one load feeds 4 FMAs - with one row per
+//           thread and 8-byte reads the kernel was bound by the shared-memory pipe at 80 us per pass), Q is
+//           read coalesced along rows, 2L FP64 FMAs per loaded element.  Partials go to a [ksplit][2L][rows]
+//           buffer.  The FMA sequence per (row, candidate) is unchanged, so are the bits.
 // Kernel 2: fixed-order reduction over the k-slices, (c/d)^2, per-CTA partial sums; the CTA that
 //           finishes last adds them in a fixed order -> Le[L].  Deterministic (the only atomic is
 //           the arrival counter), so the discrete decisions of the golden section are
@@ -31,23 +33,25 @@ __global__ void __launch_bounds__(256)
     loo_partial_kernel(const double* __restrict__ Q, long long ldq, int n_rows, int k,
                        const double* __restrict__ ev, const double* __restrict__ z, LamPack lp,
                        int ksplit, double* __restrict__ part) {
-  __shared__ double g1[LOO_JC][L];  // z_j * w_jl
-  __shared__ double g2[LOO_JC][L];  // w_jl
-  const int row = blockIdx.x * 256 + threadIdx.x;
+  constexpr int LP = (L + 1) & ~1;                   // padded to pairs for the 16-byte reads
+  __shared__ __align__(16) double g1[LOO_JC][LP];    // z_j * w_jl
+  __shared__ __align__(16) double g2[LOO_JC][LP];    // w_jl
+  const int row0 = blockIdx.x * 512 + threadIdx.x, row1 = row0 + 256;
   const int per = (k + ksplit - 1) / ksplit;
   const int kb = min(k, (int)blockIdx.y * per), ke = min(k, kb + per);
-  double c[L], d[L];
+  double c0[LP], d0[LP], c1[LP], d1[LP];
 #pragma unroll
-  for (int l = 0; l < L; ++l) c[l] = d[l] = 0.0;
-  const double* q = Q + (row < n_rows ? row : 0);
+  for (int l = 0; l < LP; ++l) c0[l] = d0[l] = c1[l] = d1[l] = 0.0;
+  const double* q0 = Q + (row0 < n_rows ? row0 : 0);
+  const double* q1 = Q + (row1 < n_rows ? row1 : 0);
 
   for (int j0 = kb; j0 < ke; j0 += LOO_JC) {
     const int jc = min(LOO_JC, ke - j0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < LOO_JC * L; idx += 256) {
-      const int jj = idx / L, l = idx % L;
+    for (int idx = threadIdx.x; idx < LOO_JC * LP; idx += 256) {
+      const int jj = idx / LP, l = idx % LP;
       double w = 0.0, zz = 0.0;
-      if (jj < jc) {
+      if (jj < jc && l < L) {
         w = 1.0 / (ev[j0 + jj] + lp.lam[l]);
         zz = z[j0 + jj];
       }
@@ -55,25 +59,40 @@ __global__ void __launch_bounds__(256)
       g2[jj][l] = w;
     }
     __syncthreads();
-    if (row < n_rows) {
-#pragma unroll 4
-      for (int jj = 0; jj < jc; ++jj) {
-        const double v = q[(long long)(j0 + jj) * ldq];
-        const double v2 = v * v;
+#pragma unroll 2
+    for (int jj = 0; jj < jc; ++jj) {
+      const double va = q0[(long long)(j0 + jj) * ldq], vb = q1[(long long)(j0 + jj) * ldq];
+      const double va2 = va * va, vb2 = vb * vb;
+      const double2* p1 = reinterpret_cast<const double2*>(&g1[jj][0]);
+      const double2* p2 = reinterpret_cast<const double2*>(&g2[jj][0]);
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-          c[l] = fma(v, g1[jj][l], c[l]);
-          d[l] = fma(v2, g2[jj][l], d[l]);
-        }
+      for (int l = 0; l < LP; l += 2) {
+        const double2 a1 = p1[l / 2], a2 = p2[l / 2];
+        c0[l] = fma(va, a1.x, c0[l]);
+        c0[l + 1] = fma(va, a1.y, c0[l + 1]);
+        d0[l] = fma(va2, a2.x, d0[l]);
+        d0[l + 1] = fma(va2, a2.y, d0[l + 1]);
+        c1[l] = fma(vb, a1.x, c1[l]);
+        c1[l + 1] = fma(vb, a1.y, c1[l + 1]);
+        d1[l] = fma(vb2, a2.x, d1[l]);
+        d1[l + 1] = fma(vb2, a2.y, d1[l + 1]);
       }
     }
   }
-  if (row < n_rows) {
-    double* o = part + (size_t)blockIdx.y * (2 * L) * (size_t)n_rows + row;
+  if (row0 < n_rows) {
+    double* o = part + (size_t)blockIdx.y * (2 * L) * (size_t)n_rows + row0;
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      o[(size_t)(2 * l) * n_rows] = c[l];
-      o[(size_t)(2 * l + 1) * n_rows] = d[l];
+      o[(size_t)(2 * l) * n_rows] = c0[l];
+      o[(size_t)(2 * l + 1) * n_rows] = d0[l];
+    }
+  }
+  if (row1 < n_rows) {
+    double* o = part + (size_t)blockIdx.y * (2 * L) * (size_t)n_rows + row1;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      o[(size_t)(2 * l) * n_rows] = c1[l];
+      o[(size_t)(2 * l + 1) * n_rows] = d1[l];
     }
   }
 }
@@ -137,7 +156,7 @@ static int loo_run(bk_ctx* ctx, const double* Q, long long ldq, int n_rows, int 
   BK_TRY(ctx->gemm_ws.ensure(part_elems + bp_elems));
   double* part = ctx->gemm_ws.p;
   double* bp = part + part_elems;
-  dim3 grid(rb, ksplit);
+  dim3 grid((unsigned)ceil_div(n_rows, 512), ksplit);
   loo_partial_kernel<L><<<grid, 256, 0, ctx->stream>>>(Q, ldq, n_rows, k, ev, z, lp, ksplit, part);
   BK_LAUNCHED(ctx);
   loo_finish_kernel<L><<<rb, 256, 0, ctx->stream>>>(part, n_rows, ksplit, bp, coeffs, ctx->counters.p, Le_dev);

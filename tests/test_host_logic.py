@@ -122,6 +122,21 @@ def host_bounds(values, n):
     return rc, L.value, U.value
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_lambda_bounds_with_signed_noise_tail(seed):
+    """A real kernel spectrum ends in rounding noise of both signs; the bounds code sums that tail through suffix sums
+    (e/(e+x) ~ e/x) and must still stop exactly where the reference's scans stop."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1500, 6000))
+    lead = int(rng.integers(40, 400))
+    ev = np.concatenate([n * np.exp(-np.arange(lead) * (8.0 / lead)), 1e-12 * n * (rng.random(n - lead) - 0.4)])
+    ev = np.sort(ev)[::-1]
+    ev[:lead] *= (n - ev[lead:].sum()) / ev[:lead].sum()
+    L0, U0 = o.lambda_bounds(ev, n)
+    rc, L, U = host_bounds(ev, n)
+    assert rc == 0 and (L, U) == (L0, U0)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_lambda_bounds_bisection_equals_linear_scan(seed):
     """The upper bound is found by gallop + bisection instead of the reference's `U <- U - 1` scan
