@@ -213,8 +213,9 @@ struct bk_ctx {
   bk::DevBuf<unsigned int> barrier;    // grid-barrier counters
   bk::DevBuf<unsigned char> scratch;   // small general scratch (descriptors, partial sums)
   bk::DevBuf<unsigned int> counters;   // 64 arrival counters, zero between kernels (last-CTA-done reductions)
-  bk::DevBuf<double> ws[5];            // cached N x N work matrices of the eigensolver (0 work copy of K,
-                                       // 1 stage-2 reflectors, 2-4 divide & conquer), released by bk_trim / bk_destroy
+  bk::DevBuf<double> ws[7];            // cached N x N work matrices of the eigensolver (0 work copy of K,
+                                       // 1 stage-2 reflectors, 2-4 divide & conquer, 5-6 its factored top level),
+                                       // released by bk_trim / bk_destroy
   uint64_t n_launches = 0;             // kernels launched through this context (bench "gpu_launches")
   bk::HostCopier* copier = nullptr;    // hostcopy.cu
 };

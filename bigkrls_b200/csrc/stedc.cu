@@ -497,6 +497,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- lazy children of the root (see stedc): R = [U 0; 0 I] per merge, on a zeroed buffer that dc_u_kernel has filled
+__global__ void dc_unit_defl_kernel(const MergeDesc* __restrict__ descs, double* __restrict__ R, long long ld) {
+  const MergeDesc m = descs[blockIdx.y];
+  const int nm = m.hi - m.lo;
+  for (int c = m.K + blockIdx.x * blockDim.x + threadIdx.x; c < nm; c += gridDim.x * blockDim.x)
+    R[(m.lo + c) + (long long)(m.lo + c) * ld] = 1.0;
+}
+// row `row` of G over the columns [c0, c0 + cnt) as a contiguous vector
+__global__ void dc_row_kernel(const double* __restrict__ G, long long ld, int row, int c0, int cnt, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+    out[i] = G[row + (long long)(c0 + i) * ld];
+}
+__global__ void dc_lazy_z_kernel(const double* __restrict__ zl, const double* __restrict__ zr, int mid, int n, double sgn,
+                                 double* __restrict__ z) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    z[i] = (i < mid) ? zl[i] : sgn * zr[i - mid];
+}
+
 // ---- dst[:, dstcol[i]] = src[:, srccol[i]] --------------------------------------------------------------
 __global__ void dc_assemble_kernel(const double* __restrict__ src, long long lds, const int* __restrict__ srccol,
                                    double* __restrict__ dst, long long ldd, const int* __restrict__ dstcol,
@@ -563,6 +581,37 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
     BK_TRY(Gm.borrow(ctx->ws[3], (size_t)n * n));
     BK_TRY(U.borrow(ctx->ws[4], (size_t)n * n));
   }
+  // Lazy children of the root.  When only a few eigenvectors are wanted the two largest merge GEMMs below the root
+  // (each (n/2) x K x K: 40 % of the whole D&C at n = 20 000) form eigenvector matrices Q1, Q2 of which the root then
+  // uses a thin slice.  Instead the children stay FACTORED, Qc = diag(G1, G2) R with G = the gathered eigenvectors of
+  // their own children and R = [U 0; 0 I] (n x n): the root takes its z from two rows G[row, :] R, applies its
+  // deflation rotations and its column gather to R, multiplies R's gathered columns by the wanted columns of its own U
+  // (the same batched GEMM as before, same zero structure) and only then goes through G: two (n/2) x want x (n/2)
+  // products.
+  bool lazy = false;
+  {
+    int cnt = 0;
+    bool halves = false;
+    for (const Node& m : merges)
+      if (m.height == height - 1) ++cnt;
+    for (const Node& m : merges)
+      if (m.height == height && m.lo == 0 && m.hi == n) halves = true;
+    int covered = 0;
+    for (const Node& m : merges)
+      if (m.height == height - 1) covered += m.hi - m.lo;
+    const char* lz = getenv("BK_DC_LAZY");
+    lazy = Z && height >= 2 && cnt == 2 && halves && covered == n && n >= 1024 && !(lz && atoi(lz) == 0);
+  }
+  // structurally possible; whether it pays is decided at the children's level, when their eigenvalues bound the number
+  // of eigenvectors the root will be asked for (interlacing: at most one more than the children have above the threshold)
+  const bool lazy_cand = lazy;
+  lazy = false;
+  DevBuf<double> GL, RL, zrow, Ycat;
+  if (lazy_cand) {
+    BK_TRY(GL.borrow(ctx->ws[5], (size_t)n * n));
+    BK_TRY(RL.borrow(ctx->ws[6], (size_t)n * n));
+    BK_TRY(zrow.alloc((size_t)3 * n));
+  }
   std::vector<double> Dh(n), zh(n);
   if (stats) *stats = StedcStats();
   std::vector<int> order(n);
@@ -587,6 +636,11 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
   };
 
   for (int h = 1; h <= height; ++h) {
+    const bool cand_lvl = lazy_cand && h == height - 1;  // the root's children: may stay factored
+    const bool lazy_root = lazy && h == height;          // the root over factored children
+    double* const Gp = cand_lvl ? GL.p : Gm.p;           // gathered columns of this level
+    double* const Up = cand_lvl ? RL.p : U.p;            // rank-one eigenvector blocks of this level
+    double* const Qsrc = lazy_root ? RL.p : Q.p;    // what the root rotates / gathers
     std::vector<Node> lvl;
     for (const Node& m : merges)
       if (m.height == h) lvl.push_back(m);
@@ -605,9 +659,23 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
     BK_TRY(upload(ctx, desc_d, descs));
     int maxn = 0;
     for (const Node& m : lvl) maxn = std::max(maxn, m.hi - m.lo);
-    dc_gather_z_kernel<<<dim3((unsigned)ceil_div(maxn, 256), nm), 256, 0, ctx->stream>>>(desc_d.p, Q.p,
-                                                                                         ld, zv.p);
-    BK_LAUNCHED(ctx);
+    if (lazy_root) {
+      // z = [last row of Q1 ; sgn * first row of Q2] with Q = diag(G1, G2) R: two row-vector x matrix products
+      const int mid = lvl[0].mid;
+      dc_row_kernel<<<64, 256, 0, ctx->stream>>>(GL.p, ld, mid - 1, 0, mid, zrow.p + 2 * (size_t)n);
+      BK_LAUNCHED(ctx);
+      BK_TRY(gemm(ctx, true, false, mid, 1, mid, 1.0, RL.p, ld, zrow.p + 2 * (size_t)n, mid, 0.0, zrow.p, mid));
+      dc_row_kernel<<<64, 256, 0, ctx->stream>>>(GL.p, ld, mid, mid, n - mid, zrow.p + 2 * (size_t)n);
+      BK_LAUNCHED(ctx);
+      BK_TRY(gemm(ctx, true, false, n - mid, 1, n - mid, 1.0, RL.p + mid + (long long)mid * ld, ld, zrow.p + 2 * (size_t)n,
+                  n - mid, 0.0, zrow.p + n, n - mid));
+      dc_lazy_z_kernel<<<64, 256, 0, ctx->stream>>>(zrow.p, zrow.p + n, mid, n, descs[0].sgn, zv.p);
+      BK_LAUNCHED(ctx);
+    } else {
+      dc_gather_z_kernel<<<dim3((unsigned)ceil_div(maxn, 256), nm), 256, 0, ctx->stream>>>(desc_d.p, Q.p,
+                                                                                           ld, zv.p);
+      BK_LAUNCHED(ctx);
+    }
     BK_CUDA(cudaMemcpyAsync(Dh.data(), Dcur.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaMemcpyAsync(zh.data(), zv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -677,8 +745,8 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
         p.m = n1;
         p.n = K;
         p.k = md.c1 + md.c2;
-        p.A = Gm.p + lo + (long long)lo * ld;
-        p.B = U.p + lo + (long long)lo * ld;
+        p.A = Gp + lo + (long long)lo * ld;
+        p.B = Up + lo + (long long)lo * ld;
         p.C = Q.p + lo + (long long)lo * ld;
         probs.push_back(p);
         vec = vec && gemm_operands_vec_ok(p.A, ld, p.B, ld);
@@ -689,8 +757,8 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
         const int back = (((lo + md.c1) & 1) && md.c1 > 0) ? 1 : 0;
         p.m = n2;
         p.k = md.c2 + md.c3 + back;
-        p.A = Gm.p + md.mid + (long long)(lo + md.c1 - back) * ld;
-        p.B = U.p + (lo + md.c1 - back) + (long long)lo * ld;
+        p.A = Gp + md.mid + (long long)(lo + md.c1 - back) * ld;
+        p.B = Up + (lo + md.c1 - back) + (long long)lo * ld;
         p.C = Q.p + md.mid + (long long)lo * ld;
         probs.push_back(p);
         vec = vec && gemm_operands_vec_ok(p.A, ld, p.B, ld);
@@ -719,13 +787,13 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
     BK_TRY(zhat_d.ensure(n));
     if (!rp.empty()) {
       dc_rot_kernel<<<dim3((unsigned)ceil_div(maxn, 128), nm), 128, 0, ctx->stream>>>(
-          desc_d.p, rp_d.p, rn_d.p, rc_d.p, rs_d.p, Q.p, ld);
+          desc_d.p, rp_d.p, rn_d.p, rc_d.p, rs_d.p, Qsrc, ld);
       BK_LAUNCHED(ctx);
     }
     {
       const long long per = (long long)maxn * maxn;
       const unsigned gx = (unsigned)std::min<long long>(ceil_div(per, 256), 8LL * ctx->sm_count);
-      dc_gather_cols_kernel<<<dim3(gx, nm), 256, 0, ctx->stream>>>(desc_d.p, gsrc_d.p, Q.p, Gm.p, ld);
+      dc_gather_cols_kernel<<<dim3(gx, nm), 256, 0, ctx->stream>>>(desc_d.p, gsrc_d.p, Qsrc, Gp, ld);
       BK_LAUNCHED(ctx);
     }
     if (maxK > 0) {
@@ -739,6 +807,7 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
         BK_CUDA(cudaMemcpyAsync(Dh.data(), Dnew.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
         BK_CUDA(cudaStreamSynchronize(ctx->stream));
         BK_TRY(finalize_values(Dh));
+        if (lazy_root) BK_TRY(Ycat.alloc((size_t)n * std::max(1, want)));
         if (!Z || want < n) {
           const MergeDesc& md = descs[0];
           const int K = md.K;
@@ -773,7 +842,8 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
               stats->merge_flops -= 2LL * (K - nwr) * ((long long)(md.mid - md.lo) * (md.c1 + md.c2) +
                                                      (long long)(md.hi - md.mid) * (md.c2 + md.c3));
             dc_assemble_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * nwr, 256), 8LL * ctx->sm_count),
-                                 256, 0, ctx->stream>>>(Q.p, ld, rsrc_d.p, Z, ldz, rdst_d.p, n, nwr);
+                                 256, 0, ctx->stream>>>(Q.p, ld, rsrc_d.p, lazy_root ? Ycat.p : Z, lazy_root ? (long long)n : ldz,
+                                                        rdst_d.p, n, nwr);
             BK_LAUNCHED(ctx);
           }
           if (!dsrc.empty()) {
@@ -781,8 +851,16 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
             BK_TRY(upload(ctx, ddst_d, ddst));
             dc_assemble_kernel<<<(unsigned)std::min<long long>(ceil_div((long long)n * (long long)dsrc.size(), 256),
                                                                8LL * ctx->sm_count),
-                                 256, 0, ctx->stream>>>(Gm.p, ld, dsrc_d.p, Z, ldz, ddst_d.p, n, (int)dsrc.size());
+                                 256, 0, ctx->stream>>>(Gm.p, ld, dsrc_d.p, lazy_root ? Ycat.p : Z, lazy_root ? (long long)n : ldz,
+                                                        ddst_d.p, n, (int)dsrc.size());
             BK_LAUNCHED(ctx);
+          }
+          if (lazy_root && want > 0) {
+            // the wanted columns are coordinates in the children's gathered bases: through G1, G2 now
+            const int mid = descs[0].mid;
+            BK_TRY(gemm(ctx, false, false, mid, want, mid, 1.0, GL.p, ld, Ycat.p, n, 0.0, Z, ldz));
+            BK_TRY(gemm(ctx, false, false, n - mid, want, n - mid, 1.0, GL.p + mid + (long long)mid * ld, ld, Ycat.p + mid, n, 0.0,
+                        Z + mid, ldz));
           }
           BK_CUDA(cudaGetLastError());
           BK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -794,16 +872,38 @@ int stedc(bk_ctx* ctx, int n, const double* d_host, const double* e_host, double
       dc_zhat_kernel<<<dim3((unsigned)ceil_div(maxK, 128), nm), 128, 0, ctx->stream>>>(
           desc_d.p, dlam_d.p, w_d.p, org_d.p, mu_d.p, zhat_d.p);
       BK_LAUNCHED(ctx);
+      if (cand_lvl) {
+        // the children's eigenvalues are known: bound the root's demand
+        BK_CUDA(cudaMemcpyAsync(Dh.data(), Dnew.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));
+        double dmax = -INFINITY;
+        bool finite = true;
+        for (int i = 0; i < n; ++i) {
+          finite = finite && std::isfinite(Dh[i]);
+          dmax = std::max(dmax, Dh[i]);
+        }
+        long long above = 0;
+        for (int i = 0; i < n; ++i)
+          if (Dh[i] >= rel_thresh * dmax) ++above;
+        const long long bound = std::min<long long>(max_want, above + 1);
+        lazy = finite && dmax > 0.0 && bound <= n / 4;
+        if (lazy) BK_CUDA(cudaMemsetAsync(RL.p, 0, sizeof(double) * (size_t)n * n, ctx->stream));
+      }
       dc_u_kernel<<<dim3((unsigned)maxK, nm), 256, 0, ctx->stream>>>(desc_d.p, dlam_d.p, org_d.p, mu_d.p,
-                                                                     zhat_d.p, grow_d.p, U.p, ld, nullptr);
+                                                                     zhat_d.p, grow_d.p, Up, ld, nullptr);
       BK_LAUNCHED(ctx);
-      BK_TRY(upload(ctx, probs_d, probs));
-      BK_TRY(gemm_batched(ctx, false, false, probs_d.p, (int)probs.size(), gm_max_m, gm_max_n, vec));
+      if (!(cand_lvl && lazy)) {
+        BK_TRY(upload(ctx, probs_d, probs));
+        BK_TRY(gemm_batched(ctx, false, false, probs_d.p, (int)probs.size(), gm_max_m, gm_max_n, vec));
+      }
     }
-    {
+    if (cand_lvl && lazy) {
+      dc_unit_defl_kernel<<<dim3((unsigned)ceil_div(maxn, 256), nm), 256, 0, ctx->stream>>>(desc_d.p, RL.p, ld);
+      BK_LAUNCHED(ctx);
+    } else {
       const long long per = (long long)maxn * maxn;
       const unsigned gx = (unsigned)std::min<long long>(ceil_div(per, 256), 8LL * ctx->sm_count);
-      dc_copy_defl_kernel<<<dim3(gx, nm), 256, 0, ctx->stream>>>(desc_d.p, Gm.p, Q.p, ld);
+      dc_copy_defl_kernel<<<dim3(gx, nm), 256, 0, ctx->stream>>>(desc_d.p, Gp, Q.p, ld);
       BK_LAUNCHED(ctx);
     }
     BK_CUDA(cudaGetLastError());

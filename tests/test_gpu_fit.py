@@ -125,3 +125,28 @@ def test_validation_errors_match_reference_messages():
         bigKRLS(y[:-1], X)
     f = bigKRLS(y, X, derivative=False, vcov_est=False)
     assert "derivatives" not in f and "vcov.est.c" not in f
+
+
+@pytest.mark.parametrize("n,p,trunc", [(1100, 3, 0.01), (2300, 4, 0.001), (3000, 6, 0.001)])
+def test_dc_factored_top_level_agrees(monkeypatch, n, p, trunc):
+    """Divide & conquer with the root's children kept factored (few eigenvectors wanted: the two largest merge GEMMs
+    are skipped, stedc.cu) against the plain tree: same eigenvalues, lambda and lastkeeper, coefficients and variances
+    at rounding level - and against the oracle at the usual tolerances."""
+    X, y = o.synthetic(n, p, 77)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("BK_DC_LAZY", flag)
+        fit = bigKRLS(y, X, eigtrunc=trunc, noisy=False)
+        out[flag] = (fit["lambda"], int(fit["lastkeeper"]), np.array(fit["K.eigenvalues"]).copy(),
+                     np.array(fit["coeffs"]).ravel().copy(), np.array(fit["vcov.est.c"]).copy(),
+                     np.array(fit["var.avgderivatives"]).ravel().copy())
+        fit.release_device()
+    a, b = out["0"], out["1"]
+    assert a[1] == b[1] and abs(a[0] / b[0] - 1) < 1e-9
+    # the root's z comes from rows of the children's eigenvector matrices, formed by a GEMM in one variant and by a
+    # row-vector product in the other: eigenvalues agree at rounding level, not bit for bit
+    assert np.max(np.abs(a[2] - b[2])) <= 1e-13 * a[2][0]
+    assert relerr(b[3], a[3]) < 1e-10 and relerr(b[4], a[4]) < 1e-10 and relerr(b[5], a[5]) < 1e-10
+    ref = o.bigkrls(y, X, eigtrunc=trunc)
+    assert b[1] == ref["lastkeeper"] and abs(b[0] / ref["lambda"] - 1) < 1e-9
+    assert relerr(b[3], np.asarray(ref["coeffs"]).ravel()) < 1e-8
