@@ -59,23 +59,35 @@ __global__ void __launch_bounds__(256)
       g2[jj][l] = w;
     }
     __syncthreads();
-#pragma unroll 2
-    for (int jj = 0; jj < jc; ++jj) {
-      const double va = q0[(long long)(j0 + jj) * ldq], vb = q1[(long long)(j0 + jj) * ldq];
-      const double va2 = va * va, vb2 = vb * vb;
-      const double2* p1 = reinterpret_cast<const double2*>(&g1[jj][0]);
-      const double2* p2 = reinterpret_cast<const double2*>(&g2[jj][0]);
+    // the loads of 8 eigen-columns are issued before their FMAs (the kernel is otherwise bound by the latency of two
+    // dependent loads per column)
+    for (int j8 = 0; j8 < jc; j8 += 8) {
+      double va[8], vb[8];
 #pragma unroll
-      for (int l = 0; l < LP; l += 2) {
-        const double2 a1 = p1[l / 2], a2 = p2[l / 2];
-        c0[l] = fma(va, a1.x, c0[l]);
-        c0[l + 1] = fma(va, a1.y, c0[l + 1]);
-        d0[l] = fma(va2, a2.x, d0[l]);
-        d0[l + 1] = fma(va2, a2.y, d0[l + 1]);
-        c1[l] = fma(vb, a1.x, c1[l]);
-        c1[l + 1] = fma(vb, a1.y, c1[l + 1]);
-        d1[l] = fma(vb2, a2.x, d1[l]);
-        d1[l + 1] = fma(vb2, a2.y, d1[l + 1]);
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = j8 + u < jc;
+        va[u] = ok ? q0[(long long)(j0 + j8 + u) * ldq] : 0.0;
+        vb[u] = ok ? q1[(long long)(j0 + j8 + u) * ldq] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j8 + u;
+        if (jj >= jc) break;
+        const double va2 = va[u] * va[u], vb2 = vb[u] * vb[u];
+        const double2* p1 = reinterpret_cast<const double2*>(&g1[jj][0]);
+        const double2* p2 = reinterpret_cast<const double2*>(&g2[jj][0]);
+#pragma unroll
+        for (int l = 0; l < LP; l += 2) {
+          const double2 a1 = p1[l / 2], a2 = p2[l / 2];
+          c0[l] = fma(va[u], a1.x, c0[l]);
+          c0[l + 1] = fma(va[u], a1.y, c0[l + 1]);
+          d0[l] = fma(va2, a2.x, d0[l]);
+          d0[l + 1] = fma(va2, a2.y, d0[l + 1]);
+          c1[l] = fma(vb[u], a1.x, c1[l]);
+          c1[l + 1] = fma(vb[u], a1.y, c1[l + 1]);
+          d1[l] = fma(vb2, a2.x, d1[l]);
+          d1[l + 1] = fma(vb2, a2.y, d1[l + 1]);
+        }
       }
     }
   }
