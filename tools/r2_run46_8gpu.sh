@@ -2,7 +2,7 @@
 # 8-GPU pass: partitioned-fit parity on 8 ranks, headline bench at N=8, config 5
 mkdir -p gpurun_out
 NG=${1:-8}
-T=r02c
+T=r02e
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NG --master-addr 127.0.0.1"
 timeout 500 $TR --master-port 29541 tests/dist_worker.py nccl > gpurun_out/${T}_dist_worker_${NG}gpu.log 2>&1; echo "worker rc=$?" >> gpurun_out/${T}_dist_worker_${NG}gpu.log
 timeout 300 $TR --master-port 29542 bench.py --gpus $NG --steps 3 --warmup 3 > gpurun_out/${T}_bench_${NG}gpu.json 2> gpurun_out/${T}_bench_${NG}gpu.err; echo "bench rc=$?" >> gpurun_out/${T}_bench_${NG}gpu.err
@@ -16,4 +16,4 @@ print('value', round(d['value'],4), 'e2e', round(d['e2e']['value'],4), 'pageable
 p=d.get('parity_vs_oracle_fixture'); print('parity ok:', all(x.get('within_tolerance') for x in p) if isinstance(p,list) else p)
 d=json.loads(open('gpurun_out/${T}_config5_${NG}gpu.json').read().strip().splitlines()[-1]); print('config5', round(d['value'],4))
 PY
-tail -2 gpurun_out/${T}_bench_${NG}gpu.err gpurun_out/${T}_config5_${NG}gpu.err
+tail -n 2 gpurun_out/${T}_bench_${NG}gpu.err
