@@ -2,7 +2,8 @@
 // one C call, with X, K, Q, Lambda, c never leaving HBM between stages.
 //
 //   1/5 kernel            gauss_kernel.cu                       (src/gauss_kernel.cpp)
-//   2/5 eigen             sytrd.cu + stedc.cu + ormtr.cu        (src/eigen.cpp, bEigen R:173-199)
+//   2/5 eigen             sy2sb.cu + sb2st.cu (two-stage) or sytrd.cu (one-stage), stedc.cu, ormtr.cu;
+//                         eigen_topk.cu for Neig << N           (src/eigen.cpp, bEigen R:173-199)
 //   3/5 lambda            golden section on the host, bit-for-bit the arithmetic of
 //                         R/bigKRLS_Rcpp_functions.R:5-82, with the LOO loss of up to 15
 //                         speculative candidates per pass over Q (loo.cu)
@@ -13,9 +14,10 @@
 //
 // Multi-GPU (one process per GPU): N x N matrices are partitioned by COLUMN BLOCKS - for the
 // symmetric K, V this is the transposed row panel, and it is contiguous in column-major
-// storage so blocks can be all-gathered in place.  The eigensolver runs on rank 0 and Q is
-// broadcast.  All collectives go through the bk_comm callbacks (NCCL via torch.distributed
-// in the Python host).
+// storage so blocks can be all-gathered in place.  Native path (peer-memory communicator, peer.cu): the dense->band
+// stage of the eigensolver and the back-transformation are distributed, the band->tridiagonal stage and the divide &
+// conquer run on every rank (same bits, nothing to broadcast); small problems and the generic bk_comm callback
+// transport (NCCL / gloo via torch.distributed in the Python host) run the eigensolver on rank 0 and broadcast Q.
 #include <algorithm>
 #include <cmath>
 #include <functional>
