@@ -216,6 +216,7 @@ struct bk_ctx {
   bk::DevBuf<double> ws[7];            // cached N x N work matrices of the eigensolver (0 work copy of K,
                                        // 1 stage-2 reflectors, 2-4 divide & conquer, 5-6 its factored top level),
                                        // released by bk_trim / bk_destroy
+  double* host_scratch = nullptr;      // 4 KB of pinned host memory for small result read-backs (LOO losses per pass)
   uint64_t n_launches = 0;             // kernels launched through this context (bench "gpu_launches")
   bk::HostCopier* copier = nullptr;    // hostcopy.cu
 };

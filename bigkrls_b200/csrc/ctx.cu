@@ -121,6 +121,7 @@ int bk_init(int device, bk_ctx** out) {
   c->panel_cache[0].plain = c->panel_cache[1].plain = true;
   c->counters.plain = true;
   BK_TRY(c->gemm_ws_side.alloc((size_t)4 << 20));
+  BK_CUDA(cudaMallocHost((void**)&c->host_scratch, 4096));
   BK_TRY(c->counters.alloc(64));
   BK_CUDA(cudaMemsetAsync(c->counters.p, 0, 64 * sizeof(unsigned), c->stream));
   *out = c;
@@ -143,6 +144,8 @@ void bk_destroy(bk_ctx* ctx) {
   ctx->barrier.release();
   ctx->scratch.release();
   ctx->counters.release();
+  if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
+  ctx->host_scratch = nullptr;
   for (auto& w : ctx->ws) w.release();
   cudaStreamSynchronize(ctx->stream);
   bk::big_cache_trim(ctx->device);

@@ -91,8 +91,8 @@ double ratio_sum_fast(const std::vector<double>& ev, double x, double* abs_terms
 // sign of (R's sum(ev/(ev+x)) - thr): -1 below, 0 equal, +1 above.  Decided by the fast sum whenever it is
 // further from the threshold than its own error bound (plus the long-double sum's), otherwise by the reference's
 // arithmetic itself - so every comparison of the bounds loops has exactly the outcome R would get.
-// Most of a kernel matrix's spectrum is rounding noise around zero: for |e| <= 1e-10 x the term e/(e+x) equals e/x up
-// to a relative 2e-10, so the tail of the (descending) spectrum enters the fast sums through suffix sums of e and |e|
+// Most of a kernel matrix's spectrum is rounding noise around zero: for |e| <= 1e-7 x the term e/(e+x) equals e/x up
+// to a relative 2e-7 (of a term that is itself below 1e-7), so the tail of the (descending) spectrum enters the fast sums through suffix sums of e and |e|
 // and only the leading part is divided out - a few hundred terms instead of Neig.  The tail's truncation error joins
 // the error band of the comparison, so the decisions stay exactly R's.
 struct RatioTail {
@@ -112,15 +112,15 @@ struct RatioTail {
       a1[i] = a1[i + 1] + std::fabs(e[i]);
     }
   }
-  // first index whose value (and, the spectrum being descending, every later POSITIVE value) is below 1e-10 x; the
+  // first index whose value (and, the spectrum being descending, every later POSITIVE value) is below 1e-7 x; the
   // negative noise behind it must be as small in magnitude for the expansion to hold: checked on the last element
   size_t cut(double x) const {
     const std::vector<double>& e = *ev;
-    if (!sorted || !(x > 0.0) || e.empty() || std::fabs(e.back()) > 1e-10 * x) return e.size();
+    if (!sorted || !(x > 0.0) || e.empty() || std::fabs(e.back()) > 1e-7 * x) return e.size();
     size_t lo = 0, hi = e.size();
     while (lo < hi) {
       const size_t mid = lo + (hi - lo) / 2;
-      if (e[mid] < 1e-10 * x) hi = mid; else lo = mid + 1;
+      if (e[mid] < 1e-7 * x) hi = mid; else lo = mid + 1;
     }
     return lo;
   }
@@ -140,7 +140,7 @@ int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
       const double tail = g_tail.s1[c] / x, tail_abs = g_tail.a1[c] / x;
       const double f = ((s[0] + s[1]) + (s[2] + s[3])) + tail;
       const double at = ((a[0] + a[1]) + (a[2] + a[3])) + tail_abs;
-      const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 4 + 8) * at + 4e-10 * tail_abs +
+      const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 4 + 8) * at + 4e-7 * tail_abs +
                           1e-13 * std::fabs(thr);
       if (std::isfinite(f) && std::fabs(f - thr) > band) return f < thr ? -1 : 1;
       const double sx = (double)ratio_sum(ev, x);
@@ -623,11 +623,27 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
   DevBuf<double> z, Le_dev;
   BK_TRY(z.alloc(k));
   BK_TRY(Le_dev.alloc(16));
+  const bool lprof = getenv("BK_LAMBDA_PROF") != nullptr;
+  auto now_us = []() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  };
+  double tp[6] = {0, 0, 0, 0, 0, 0};
+  if (lprof) {
+    cudaStreamSynchronize(ctx->stream);
+    tp[0] = now_us();
+  }
   BK_TRY(gemm(ctx, true, false, k, 1, n, 1.0, f->Q.p, ld, f->y.p, ld, 0.0, z.p, k));
+  if (lprof) {
+    cudaStreamSynchronize(ctx->stream);
+    tp[1] = now_us();
+  }
   double lam = o.lambda;
   if (!(lam > 0.0)) {
     double L = o.L, U = o.U;
     BK_TRY(lambda_bounds(f->evals, n, &L, &U));
+    if (lprof) tp[2] = now_us();
     const double tol = (o.tol > 0.0) ? o.tol : 1e-3 * n;  // R:10-12 (bigKRLS() never forwards tol)
     LooEvaluator le;
     const double* Qpanel = f->Q.p + f->c0;
@@ -638,19 +654,41 @@ int run_fit(bk_fit* f, const bk_comm* comm) {
         BK_TRY(peer_allreduce_sum(peer, Le_dev.p, 16, ctx->stream));
       else if (multi)
         COMM_CALL(comm->allreduce_sum(comm->user, Le_dev.p, 16), "allreduce(Le)");
-      BK_CUDA(cudaMemcpyAsync(out, Le_dev.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+      // pinned landing buffer: a pageable destination makes the copy a staged, blocking one (20-30 us per pass)
+      BK_CUDA(cudaMemcpyAsync(ctx->host_scratch, Le_dev.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
       BK_CUDA(cudaStreamSynchronize(ctx->stream));
+      memcpy(out, ctx->host_scratch, sizeof(double) * 16);
       return BK_OK;
     };
     le.batch = std::max(1, std::min(15, o.loo_batch > 0 ? o.loo_batch : 15));
     BK_TRY(lambda_search(le, L, U, tol, &lam, &f->n_probes));
     f->n_passes = le.passes;
+    if (lprof) tp[3] = now_us();
   }
   f->lambda = lam;
   {
-    long double s = 0.0L;  // R/bigKRLS.R:280 (all Neig eigenvalues)
-    for (double e : f->evals) s += (long double)(e / (e + lam));
+    // R/bigKRLS.R:280 (all Neig eigenvalues, R's long-double sum).  The noise tail of the spectrum (|e| <= 1e-10 lam)
+    // enters through its plain sum: e/(e+lam) = e/lam to a relative 1e-10, far below the 1e-8 the value is compared at
+    long double s = 0.0L;
+    size_t cut = f->evals.size();
+    bool sorted = true;
+    for (size_t i = 1; i < f->evals.size() && sorted; ++i) sorted = f->evals[i] <= f->evals[i - 1];
+    if (sorted && !f->evals.empty() && std::fabs(f->evals.back()) <= 1e-10 * lam) {
+      cut = (size_t)(std::partition_point(f->evals.begin(), f->evals.end(), [&](double e) { return e >= 1e-10 * lam; }) -
+                     f->evals.begin());
+    }
+    for (size_t i = 0; i < cut; ++i) s += (long double)(f->evals[i] / (f->evals[i] + lam));
+    if (cut < f->evals.size()) {
+      double tail = 0.0;
+      for (size_t i = cut; i < f->evals.size(); ++i) tail += f->evals[i];
+      s += (long double)(tail / lam);
+    }
     f->neffective = (double)((long double)n - s);
+  }
+  if (lprof) {
+    tp[4] = now_us();
+    fprintf(stderr, "[lambda prof] Q'y %.0f us, bounds %.0f us, search %.0f us (%d passes), neffective %.0f us\n", tp[1] - tp[0],
+            tp[2] - tp[1], tp[3] - tp[2], f->n_passes, tp[4] - tp[3]);
   }
   f->info.t_lambda = tm.stop();
 

@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(256)
     loo_finish_kernel(const double* __restrict__ part, int n_rows, int ksplit,
                       double* __restrict__ blockpart, double* __restrict__ coeffs,
                       unsigned* __restrict__ done, double* __restrict__ Le) {
-  __shared__ double red[32];
   __shared__ bool last;
   const int row = blockIdx.x * 256 + threadIdx.x;
   double e[L];
@@ -134,10 +133,23 @@ __global__ void __launch_bounds__(256)
       if (l == 0 && coeffs) coeffs[row] = c;
     }
   }
+  // per-CTA sums of all L candidates with ONE barrier (a block_sum per candidate cost 3 barriers each): warp sums by
+  // shuffles, then thread l adds the 8 warp sums in warp order - fixed order, deterministic
+  {
+    __shared__ double wsum[8][L];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
-    const double s = block_sum(e[l], red);
-    if (threadIdx.x == 0) blockpart[(size_t)blockIdx.x * L + l] = s;
+    for (int l = 0; l < L; ++l) {
+      const double s = warp_sum(e[l]);
+      if (lane == 0) wsum[wid][l] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < L) {
+      double s = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += wsum[w8][threadIdx.x];
+      blockpart[(size_t)blockIdx.x * L + threadIdx.x] = s;
+    }
   }
   // the CTA that finishes last adds the per-CTA sums in a FIXED order (deterministic: the golden section is a
   // discrete decision path) - this used to be a third launch
