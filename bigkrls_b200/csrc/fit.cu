@@ -95,6 +95,7 @@ double ratio_sum_fast(const std::vector<double>& ev, double x, double* abs_terms
 // to a relative 2e-7 (of a term that is itself below 1e-7), so the tail of the (descending) spectrum enters the fast sums through suffix sums of e and |e|
 // and only the leading part is divided out - a few hundred terms instead of Neig.  The tail's truncation error joins
 // the error band of the comparison, so the decisions stay exactly R's.
+static int g_cmp_calls = 0, g_cmp_exact = 0;  // BK_LAMBDA_PROF
 struct RatioTail {
   const std::vector<double>* ev = nullptr;
   bool sorted = false;
@@ -142,7 +143,9 @@ int ratio_cmp(const std::vector<double>& ev, double x, double thr) {
       const double at = ((a[0] + a[1]) + (a[2] + a[3])) + tail_abs;
       const double band = 4.0 * 2.220446049250313e-16 * (double)(ev.size() / 4 + 8) * at + 4e-7 * tail_abs +
                           1e-13 * std::fabs(thr);
+      ++g_cmp_calls;
       if (std::isfinite(f) && std::fabs(f - thr) > band) return f < thr ? -1 : 1;
+      ++g_cmp_exact;
       const double sx = (double)ratio_sum(ev, x);
       return sx < thr ? -1 : (sx > thr ? 1 : 0);
     }
@@ -164,10 +167,23 @@ double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
   for (int it = 0; it < 12; ++it) {
     double f = 0.0, g = 0.0;
     const size_t c = tail_ok ? g_tail.cut(x) : ev.size();
-    for (size_t i = 0; i < c; ++i) {
-      const double e = ev[i], d = e + x, r = e / d;
-      f += r;
-      g -= r / d;
+    {
+      // four independent accumulator pairs: the divisions pipeline instead of waiting for one dependent add chain
+      double fa[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0};
+      size_t i = 0;
+      for (; i + 4 <= c; i += 4)
+        for (int u = 0; u < 4; ++u) {
+          const double e = ev[i + u], d = e + x, r = e / d;
+          fa[u] += r;
+          ga[u] -= r / d;
+        }
+      for (; i < c; ++i) {
+        const double e = ev[i], d = e + x, r = e / d;
+        fa[0] += r;
+        ga[0] -= r / d;
+      }
+      f = (fa[0] + fa[1]) + (fa[2] + fa[3]);
+      g = (ga[0] + ga[1]) + (ga[2] + ga[3]);
     }
     if (c < ev.size()) {  // the noise tail: e/(e+x) ~ e/x (a starting guess only)
       f += g_tail.s1[c] / x;
@@ -186,6 +202,22 @@ double ratio_root_guess(const std::vector<double>& ev, double thr, double x0) {
 }
 
 int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
+  const bool bprof = getenv("BK_LAMBDA_PROF") != nullptr;
+  auto now_us = []() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  };
+  const double tb0 = bprof ? now_us() : 0.0;
+  g_cmp_calls = g_cmp_exact = 0;
+  struct ProfEnd {
+    bool on;
+    double t0;
+    std::function<double()> now;
+    ~ProfEnd() {
+      if (on) fprintf(stderr, "[lambda bounds prof] %.0f us, %d comparisons of which %d by the exact long-double sum\n", now() - t0, g_cmp_calls, g_cmp_exact);
+    }
+  } prof_end{bprof, tb0, now_us};
   g_tail.build(ev);
   struct TailReset {
     ~TailReset() { g_tail.ev = nullptr; }
@@ -201,7 +233,15 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
       hi = 0;
     } else if ([&]() {
                  // Newton guess for the crossing, then the scan's own stopping rule on the two neighbouring integers
-                 const double xr = ratio_root_guess(ev, 1.0, 0.5 * (double)n);
+                 // sum e/(e+U) = 1 with U far above most of the spectrum: U ~ sum e - sum e^2 / U ~ tr - sum e^2 / tr
+                 double tr = 0.0, tr2 = 0.0;
+                 for (double e : ev) {
+                   tr += e;
+                   tr2 += e * e;
+                 }
+                 double x0 = (tr > 0.0) ? tr - tr2 / tr : 0.5 * (double)n;
+                 if (!(x0 > 1.0) || !(x0 < (double)n)) x0 = 0.5 * (double)n;
+                 const double xr = ratio_root_guess(ev, 1.0, x0);
                  if (!(xr > 1.0) || !(xr < (double)n)) return false;
                  for (long long m = (long long)n - (long long)std::floor(xr) - 1, t = 0; t < 3; ++m, ++t) {
                    if (m < 1 || m > (long long)n - 1) continue;
@@ -259,7 +299,9 @@ int lambda_bounds(const std::vector<double>& ev, int n, double* L, double* U) {
     size_t lo = 0, hi = 0;
     bool found = stop(0);
     if (!found) {
-      const double xr = ratio_root_guess(ev, (double)q, 1.0);
+      // about q eigenvalues lie above the root: start at the q-th largest (the spectrum is sorted when the tail is)
+      const double xs = (g_tail.sorted && q >= 1 && (size_t)q <= ev.size() && ev[q - 1] > 0.0) ? ev[q - 1] : 1.0;
+      const double xr = ratio_root_guess(ev, (double)q, xs);
       if (xr > 0.0 && xr < 4e6) {
         const long long i0 = (long long)std::ceil((xr - ls[0]) / 0.05);
         for (long long i = std::max(1LL, i0 - 1), t = 0; t < 3 && !found; ++i, ++t)
