@@ -1285,6 +1285,280 @@ __global__ void __launch_bounds__(2 * WC + 32, (WC <= 48) ? 3 : (WC <= 80 ? 2 : 
   if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[6] = clock64() - tk0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Q2 back-transformation on the FP64 tensor path (q2_mma_kernel): 8 sweeps of a hop index as one block reflector
+// ---------------------------------------------------------------------------------------------------------
+// The kernel above applies one reflector after the other with one (half) column per thread: every thread reads
+// every reflector entry from shared memory, and that broadcast traffic bounds it (ncu, profiles/r02g_q2_ncu_key.txt:
+// 55 % of the warp samples at barriers, shared-memory data pipe 70 % busy in a CTA that computes, FP64 pipe 14 %).
+// Here a pass of hop index t covers the 8 sweeps jp .. jp-7 (jp = jmax(t) - 8 i; sweeps below 0 are identity
+// reflectors): their union of rows is the 72-row window  row(w) = lo - 7 + w,  lo = jp + 1 + 64 t,  reflector s on
+// w = 7-s .. 70-s.  With V (72 x 8, zero-padded) and the compact-WY factor T (8 x 8 upper triangular,
+// q2_tfac8_kernel) the pass is  Z_w <- Z_w - V T' (V' Z_w),  three small products that run as DMMA.8x8x4 on
+// TRANSPOSED tiles so that the window never changes registers:
+//   a warp owns 16 columns (2 tiles of 8); lane l of tile c holds z[c][2j+e] = Z(row(8j + 2(l%4) + e), col 8c + l/4),
+//   j = 0..8 - this is at once the A fragment of k-step q = 2j+e of  D' = Z_w' V  (the k index runs over the rows in
+//   the order 8j + 2k + e, the B fragments are staged in the same order) and the C fragment of row tile j of
+//   Z_w' -= W' V'  (W' = D' T, whose C fragment is again the A fragment of the next product under the same
+//   permutation of the reflector index).  No shuffles, no transposition; the reflectors are read from shared memory
+//   once per 16 columns and 8 sweeps (40 x 256 B per warp) instead of once per column and sweep.
+//   Between passes the window moves down by exactly one row tile (registers renamed), tile 8 (rows lo+57 .. lo+64)
+//   retires to global memory - it is tile 0 of hop index t+1 at the pass with the same jp (jmax(t+1) = jmax(t) - 64:
+//   the passes of all hop indices lie on one lattice) - and tile 0 of the next pass comes in from global memory.
+//   done[t] = jp after the pass: hop index t+1 may run the pass with that jp.  Rows below 1 + 64 t never belong to hop
+//   index t (only the zero-padded last pass sees them): neither loaded nor stored.
+// The fragments of a pass (B operands of the three products, in fragment order: 18 + 18 + 2 warp-wide 8-byte loads)
+// arrive by cp.async, zero-filled where a reflector has no entry, three passes deep.
+static constexpr int Q2M_PB = 18 * 32 + 9 * 64 + 64;  // doubles per staged pass: dots, update, triangular factor
+static constexpr int Q2M_NB = 3;                      // staged passes in flight
+
+struct Q2MArgs {
+  double* Zt;     // kc x n (ld = ldzt)
+  long long ldzt;
+  int n, kc;
+  const double* VV;
+  const double* TAU;
+  int maxhops;
+  int* done;            // per hop index: jp of the last finished pass (INT_MAX initially)
+  const double* TF;     // per (hop index, pass): T in B-fragment order (64 doubles)
+  const long long* offs;  // first pass of hop index t in TF
+};
+
+// T of the 8 reflectors of (hop index t, pass i), forward column-wise recurrence of the compact-WY form:
+// T[s][s] = tau_s, T[0:s, s] = -tau_s T[0:s, 0:s] (V[:, 0:s]' v_s).  One warp per pass; output in the order the
+// kernel reads it as B fragments of W' = D' T: entry 32 e + l = T[2 (l%4) + e][l/4].
+__global__ void __launch_bounds__(256) q2_tfac8_kernel(const double* __restrict__ VV, const double* __restrict__ TAU,
+                                                       int maxhops, int n, const long long* __restrict__ offs,
+                                                       double* __restrict__ TF) {
+  __shared__ double tsm[8][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t = blockIdx.y, jmax = n - 3 - t * CB, np = jmax / 8 + 1;
+  const int i = blockIdx.x * 8 + wid;
+  if (i >= np) return;
+  const int jp = jmax - 8 * i, lo = jp + 1 + t * CB;
+  double v[8][3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int w = lane + 32 * q, row = lo - 7 + w;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int vi = w - (7 - s);
+      v[s][q] = (w < 72 && jp - s >= 0 && vi >= 0 && vi < CB && row < n) ? VV[(size_t)row + (size_t)(jp - s) * n] : 0.0;
+    }
+  }
+  double tau[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) tau[s] = (jp - s >= 0) ? TAU[t + (size_t)(jp - s) * maxhops] : 0.0;
+  double T[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int s = 0; s < 8; ++s) T[r][s] = 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    double g[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < s) {
+        double x = fma(v[r][0], v[s][0], fma(v[r][1], v[s][1], v[r][2] * v[s][2]));
+        g[r] = warp_sum(x);
+      }
+    }
+    T[s][s] = tau[s];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < s) {
+        double x = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c >= r && c < s) x = fma(T[r][c], g[c], x);
+        T[r][s] = -tau[s] * x;
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int s = 0; s < 8; ++s) tsm[wid][r * 8 + s] = T[r][s];
+  }
+  __syncwarp();
+  double* o = TF + (size_t)(offs[t] + i) * 64;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) o[32 * e + lane] = tsm[wid][(2 * (lane & 3) + e) * 8 + (lane >> 2)];
+}
+
+template <int NW>  // compute warps of 16 columns each, plus one warp for the flags
+__global__ void __launch_bounds__(32 * NW + 32, (NW <= 3) ? 3 : (NW <= 5 ? 2 : 1)) q2_mma_kernel(Q2MArgs a) {
+  constexpr int NT = 2;
+  constexpr int NCT = 32 * NW;  // compute threads
+  extern __shared__ __align__(16) double q2m_sm[];  // Q2M_NB staged passes
+  const int n = a.n, kc = a.kc, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, l4 = lane >> 2, lm = lane & 3;
+  const bool comp = warp < NW;
+  const bool flagger = (tid == NCT);
+  const int nhop = (n - 3) / CB + 1;
+  const double* const VV = a.VV;
+  int colg[NT];
+  bool act[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) {
+    colg[c] = warp * (8 * NT) + 8 * c + l4;
+    act[c] = comp && colg[c] < kc;
+  }
+  for (int t = blockIdx.x; t < nhop; t += gridDim.x) {
+    const int jmax = n - 3 - t * CB, np = jmax / 8 + 1;
+    const int rmin = 1 + t * CB;  // first row that ever belongs to this hop index
+    const int* pdone = a.done + t - 1;
+    int* mydone = a.done + t;
+    const double* const tf = a.TF + (size_t)a.offs[t] * 64;
+    // cp.async of the fragments of pass i into its ring slot (compute threads; everybody commits)
+    auto stage = [&](int i) {
+      if (comp && i < np) {
+        const int jp = jmax - 8 * i, lo = jp + 1 + t * CB;
+        double* buf = q2m_sm + (i % Q2M_NB) * Q2M_PB;
+        for (int e = tid; e < Q2M_PB; e += NCT) {
+          const double* src = VV;
+          int bytes = 0;
+          if (e < 1152) {
+            int s, w;
+            if (e < 576) {  // dots: k-step q = 2j+ee, lane l: V(w = 8j + 2(l%4) + ee, s = l/4)
+              const int q = e >> 5, l = e & 31;
+              s = l >> 2;
+              w = 8 * (q >> 1) + 2 * (l & 3) + (q & 1);
+            } else {  // update: row tile j, k-step ee, lane l: V(w = 8j + l/4, s = 2(l%4) + ee)
+              const int e2 = e - 576, l = e2 & 31;
+              s = 2 * (l & 3) + ((e2 >> 5) & 1);
+              w = 8 * (e2 >> 6) + (l >> 2);
+            }
+            const int vi = w - (7 - s), row = lo - 7 + w, sw = jp - s;
+            if (sw >= 0 && vi >= 0 && vi < CB && row < n) {
+              src = VV + (size_t)row + (size_t)sw * n;
+              bytes = 8;
+            }
+          } else {
+            src = tf + (size_t)i * 64 + (e - 1152);
+            bytes = 8;
+          }
+          cp_async8(buf + e, src, bytes);
+        }
+      }
+      cp_async_commit();
+    };
+    auto wait_pass = [&](int i) {  // hop index t-1 has finished the pass with the same jp
+      if (t > 0 && flagger && i < np) {
+        const int jp = jmax - 8 * i;
+        while (ld_acquire_i32(pdone) > jp) {
+        }
+      }
+    };
+    wait_pass(0);
+    wait_pass(1);
+    stage(0);
+    stage(1);
+    __syncthreads();  // passes 0 and 1 of hop index t-1 are finished: their retired rows may be read
+    double z[NT][18];
+    {
+      const int lo = jmax + 1 + t * CB;
+#pragma unroll
+      for (int c = 0; c < NT; ++c)
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int row = lo - 7 + 8 * j + 2 * lm + e;
+            z[c][2 * j + e] = (act[c] && row >= rmin && row < n) ? __ldcg(a.Zt + colg[c] + (size_t)row * a.ldzt) : 0.0;
+          }
+    }
+    cp_async_wait<1>();
+    __syncthreads();  // the fragments of pass 0 are visible
+    for (int i = 0; i < np; ++i) {
+      const int jp = jmax - 8 * i, lo = jp + 1 + t * CB;
+      const bool last = (i == np - 1);
+      stage(i + 2);  // its slot was read in pass i-1
+      // tile 0 of the next pass: rows lo-15 .. lo-8 (retired by hop index t-1 in its pass jp-8, verified before the
+      // barrier that ended pass i-1)
+      double nr[NT][2];
+#pragma unroll
+      for (int c = 0; c < NT; ++c)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int row = lo - 15 + 2 * lm + e;
+          nr[c][e] = (!last && act[c] && row >= rmin) ? __ldcg(a.Zt + colg[c] + (size_t)row * a.ldzt) : 0.0;
+        }
+      if (comp) {
+        const double* buf = q2m_sm + (i % Q2M_NB) * Q2M_PB;
+        // D' = Z_w' V: 18 k-steps, two accumulator pairs per tile (even / odd k-steps)
+        double d[NT][2][2];
+#pragma unroll
+        for (int c = 0; c < NT; ++c) d[c][0][0] = d[c][0][1] = d[c][1][0] = d[c][1][1] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 18; ++q) {
+          const double bv = buf[q * 32 + lane];
+#pragma unroll
+          for (int c = 0; c < NT; ++c) dmma884(d[c][q & 1][0], d[c][q & 1][1], z[c][q], bv);
+        }
+        // W' = D' T, negated
+        const double tb0 = buf[1152 + lane], tb1 = buf[1184 + lane];
+        double wn[NT][2];
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {
+          double w0 = 0.0, w1 = 0.0;
+          dmma884(w0, w1, d[c][0][0] + d[c][1][0], tb0);
+          dmma884(w0, w1, d[c][0][1] + d[c][1][1], tb1);
+          wn[c][0] = -w0;
+          wn[c][1] = -w1;
+        }
+        // Z_w' -= W' V', row tile by row tile
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const double bu0 = buf[576 + j * 64 + lane], bu1 = buf[576 + j * 64 + 32 + lane];
+#pragma unroll
+          for (int c = 0; c < NT; ++c) {
+            dmma884(z[c][2 * j], z[c][2 * j + 1], wn[c][0], bu0);
+            dmma884(z[c][2 * j], z[c][2 * j + 1], wn[c][1], bu1);
+          }
+        }
+        // tile 8 retires (tile 0 of hop index t+1 in its pass jp)
+#pragma unroll
+        for (int c = 0; c < NT; ++c)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int row = lo + 57 + 2 * lm + e;
+            if (act[c] && row < n) a.Zt[colg[c] + (size_t)row * a.ldzt] = z[c][16 + e];
+          }
+        if (last) {
+          // the rest of the window is final as well
+#pragma unroll
+          for (int c = 0; c < NT; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int row = lo - 7 + 8 * j + 2 * lm + e;
+                if (act[c] && row >= rmin && row < n) a.Zt[colg[c] + (size_t)row * a.ldzt] = z[c][2 * j + e];
+              }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NT; ++c) {
+#pragma unroll
+            for (int j = 8; j >= 1; --j) {
+              z[c][2 * j] = z[c][2 * j - 2];
+              z[c][2 * j + 1] = z[c][2 * j - 1];
+            }
+            z[c][0] = nr[c][0];
+            z[c][1] = nr[c][1];
+          }
+        }
+      }
+      cp_async_wait<1>();  // this thread's copies of pass i+1 have landed
+      wait_pass(i + 2);
+      __syncthreads();
+      if (flagger) st_release_i32(mydone, jp);  // cumulative over the barrier: the retired rows of the pass are visible
+    }
+  }
+}
+
 __global__ void transpose_kernel(const double* __restrict__ src, long long lds, int rows, int cols,
                                  double* __restrict__ dst, long long ldd) {
   __shared__ double tile[32][33];
@@ -1314,9 +1588,32 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
   BK_TRY(done.alloc(nhop));
   // kernel variant by chunk width; CTAs that can be resident at once (the pipeline over hop indices needs them all)
   const int wc = (KC <= 48) ? 48 : (KC <= 80 ? 80 : Q2_KC);
-  void* kern = (wc == 48) ? (void*)q2_apply_kernel<48> : (wc == 80 ? (void*)q2_apply_kernel<80> : (void*)q2_apply_kernel<Q2_KC>);
-  const size_t smem = sizeof(double) * Q2_ROWS * wc;
-  const int nthreads = 2 * wc + 32;
+  static const bool use_mma = !(getenv("BK_Q2_MMA") && atoi(getenv("BK_Q2_MMA")) == 0);  // 0: the one-reflector-at-a-time kernel
+  void* kern;
+  size_t smem;
+  int nthreads;
+  DevBuf<double> TF;
+  DevBuf<long long> offs;
+  if (use_mma) {
+    kern = (wc == 48) ? (void*)q2_mma_kernel<3> : (wc == 80 ? (void*)q2_mma_kernel<5> : (void*)q2_mma_kernel<10>);
+    smem = sizeof(double) * Q2M_NB * Q2M_PB;
+    nthreads = 2 * wc + 32;
+    // triangular factors of the 8-sweep block reflectors (one table for all column chunks)
+    std::vector<long long> hoffs(nhop + 1, 0);
+    for (int t = 0; t < nhop; ++t) hoffs[t + 1] = hoffs[t] + (n - 3 - t * CB) / 8 + 1;
+    BK_TRY(offs.alloc(nhop + 1));
+    BK_TRY(TF.alloc((size_t)hoffs[nhop] * 64));
+    BK_CUDA(cudaMemcpyAsync(offs.p, hoffs.data(), sizeof(long long) * (nhop + 1), cudaMemcpyHostToDevice, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));  // hoffs is a stack object
+    dim3 tg((unsigned)ceil_div((n - 3) / 8 + 1, 8), (unsigned)nhop);
+    q2_tfac8_kernel<<<tg, 256, 0, ctx->stream>>>(VV, TAU, maxhops, n, offs.p, TF.p);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(cudaGetLastError());
+  } else {
+    kern = (wc == 48) ? (void*)q2_apply_kernel<48> : (wc == 80 ? (void*)q2_apply_kernel<80> : (void*)q2_apply_kernel<Q2_KC>);
+    smem = sizeof(double) * Q2_ROWS * wc;
+    nthreads = 2 * wc + 32;
+  }
   BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
@@ -1339,12 +1636,23 @@ int q2_apply(bk_ctx* ctx, const double* VV, const double* TAU, int maxhops, int 
     a.done = done.p;
     DevBuf<long long> prof;
     a.prof = nullptr;
-    if (getenv("BK_Q2_PROF")) {
+    if (getenv("BK_Q2_PROF") && !use_mma) {
       BK_TRY(prof.alloc(8));
       BK_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(long long), ctx->stream));
       a.prof = prof.p;
     }
-    void* kargs[] = {&a};
+    Q2MArgs am;
+    am.Zt = Zt.p;
+    am.ldzt = kc;
+    am.n = n;
+    am.kc = kc;
+    am.VV = VV;
+    am.TAU = TAU;
+    am.maxhops = maxhops;
+    am.done = done.p;
+    am.TF = TF.p;
+    am.offs = offs.p;
+    void* kargs[] = {use_mma ? (void*)&am : (void*)&a};
     const int G = std::min(ctx->sm_count * per_sm, nhop);
     BK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(nthreads), kargs, smem, ctx->stream));
     BK_LAUNCHED(ctx);
