@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 closing 1-GPU pass: smoke(), full GPU test-suite, headline bench, reference arm (bounded)
 mkdir -p gpurun_out
-T=r02f
+T=${1:-r02f}
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -2 gpurun_out/${T}_pytest_gpu.log
 timeout 600 python bench.py --steps 4 --warmup 3 > gpurun_out/${T}_bench_N20000.json 2> gpurun_out/${T}_bench.err; tail -1 gpurun_out/${T}_bench.err
