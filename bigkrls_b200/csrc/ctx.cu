@@ -272,6 +272,42 @@ __global__ void __launch_bounds__(256) dmma_dfma_mix_kernel(double* out, int ite
   if (s == 123.456) out[0] = s;
 }
 
+// Latencies of dependent FP64 operations, one warp on one SM, cycles per operation measured with clock64():
+// which = 0 DFMA, 1 DMMA.8x8x4 (accumulator chain), 2 DADD, 3 64-bit shuffle (two SHFL) + DADD, 4 shared-memory
+// round trip (store, load of the neighbour's value).  The chains of the chasing kernel, the panel QR and the divide &
+// conquer are made of these.
+__global__ void __launch_bounds__(32) fp64_latency_kernel(double* out, int which, int iters) {
+  __shared__ double sm[64];
+  double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0000001, c = 1e-12, c1 = 0.0;
+  sm[threadIdx.x] = a;
+  __syncwarp();
+  const long long t0 = clock64();
+  if (which == 0) {
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) a = fma(a, b, c);
+  } else if (which == 1) {
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) dmma884(a, c1, b, c);
+  } else if (which == 2) {
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) a = a + c;
+  } else if (which == 3) {
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) a = a + __shfl_xor_sync(0xffffffffu, a, 1);
+  } else {
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+      sm[threadIdx.x] = a;
+      __syncwarp();
+      a = sm[threadIdx.x ^ 1] + c;
+      __syncwarp();
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = (double)(t1 - t0) / iters;
+  if (a + c1 == 123.456) out[1] = a;
+}
+
 __global__ void copy_peak_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                  long long n2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2;
@@ -440,6 +476,20 @@ int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result
                                        : (double)blocks * 8.0 * 16.0 * iters * 512.0;
       *result = flops / s * 1e-12;
     }
+    return BK_OK;
+  }
+  if (kind == 7) {  // size = which (see fp64_latency_kernel); returns cycles per dependent operation
+    BK_TRY(buf.alloc(16));
+    if (iters <= 0) iters = 4096;
+    double h[2] = {0.0, 0.0};
+    for (int rep = 0; rep < 2; ++rep) {
+      bk::fp64_latency_kernel<<<1, 32, 0, ctx->stream>>>(buf.p, (int)size, iters);
+      BK_LAUNCHED(ctx);
+      BK_CUDA(cudaGetLastError());
+      BK_CUDA(cudaMemcpyAsync(h, buf.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *result = h[0];
     return BK_OK;
   }
   if (kind == 6) {

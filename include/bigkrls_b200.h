@@ -249,7 +249,8 @@ BK_API int bk_fit_predict_full(const bk_fit* f, const double* newXs, int64_t m, 
 
 /* ---- test / measurement hooks ---------------------------------------------------------- */
 /* FP64 micro-benchmarks used to establish the roofline denominators (tools/):
- * kind 0: DFMA issue-bound loop, 1: DMMA m8n8k4 loop, 2: HBM copy.  Returns TFLOP/s or GB/s. */
+ * kind 0: DFMA issue-bound loop, 1: DMMA m8n8k4 loop, 2: HBM copy.  Returns TFLOP/s or GB/s.
+ * kind 7: latency in cycles of a dependent chain (size = 0 DFMA, 1 DMMA, 2 DADD, 3 shuffle + DADD, 4 shared-memory round trip). */
 BK_API int bk_microbench(bk_ctx* ctx, int kind, int64_t size, int iters, double* result);
 /* Time (device seconds, CUDA events) of `iters` runs of the library DGEMM on device-
  * generated data: C(m x n) = alpha op(A) op(B) + beta C; lower = 1 computes only the tiles on/below the

@@ -16,6 +16,9 @@ for kind, name in ((0, "dfma_tflops"), (1, "dmma_tflops"), (2, "hbm_copy_gbs"), 
                    (4, "hbm_read_tma_ring_gbs")):
     _lib.check(lib.bk_microbench(ctx.handle, kind, 0, 0, C.byref(r)))
     out[name] = r.value
+for which, name in ((0, "dfma"), (1, "dmma884"), (2, "dadd"), (3, "shfl64_dadd"), (4, "smem_roundtrip_dadd")):
+    _lib.check(lib.bk_microbench(ctx.handle, 7, which, 0, C.byref(r)))
+    out.setdefault("dependent_chain_latency_cycles", {})[name] = r.value
 if "--peaks-only" in sys.argv:
     print(json.dumps(out, indent=1))
     sys.exit(0)
