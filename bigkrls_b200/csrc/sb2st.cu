@@ -1287,6 +1287,7 @@ __global__ void __launch_bounds__(2 * WC + 32, (WC <= 48) ? 3 : (WC <= 80 ? 2 : 
 
 // ---------------------------------------------------------------------------------------------------------
 // Q2 back-transformation on the FP64 tensor path (q2_mma_kernel): 8 sweeps of a hop index as one block reflector
+// Executable specification: tests/q2_mma_prototype.py (lane-level fragments, staged pass buffers, pass lattice).
 // ---------------------------------------------------------------------------------------------------------
 // The kernel above applies one reflector after the other with one (half) column per thread: every thread reads
 // every reflector entry from shared memory, and that broadcast traffic bounds it (ncu, profiles/r02g_q2_ncu_key.txt:
